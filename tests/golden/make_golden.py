@@ -1,0 +1,234 @@
+#!/usr/bin/env python
+"""Generate the golden vectors under tests/golden/ FROM THE REAL REFERENCE MODULES.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+It path-imports the reference's src/models/base.py and src/models/loss.py (oracle/ref_import.py),
+runs them on seeded inputs and stores inputs + outputs as .npz.  The GPU box has no reference
+tree; tests there compare the CUDA path with these committed vectors.
+
+Files written
+  pair_golden.npz        measure x loss x shape: x, y, labels -> sim, probs, loss, dx, dy
+  head_golden.npz        VecSimClassificationHead (with dense+tanh) and TwoTowerClassificationHead
+  retrieval_golden.npz   all-pairs scores by the reference's pairwise modules + stable top-k
+  submit_golden.npz      submit/deepAI_result.jsonl scores/thresholds/labels (known answer: 5319
+                         positives of 15909) and the commented softmax-head weights of
+                         submit/similarity.py:5-18 with outputs of its numpy body (:19-24)
+"""
+import json
+import os
+import re
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import ref_import  # noqa: E402
+
+torch.manual_seed(20221009)
+torch.set_num_threads(1)
+base = ref_import.base()
+rloss = ref_import.loss()
+REF = ref_import.reference_dir()
+
+
+def cfg(measure, hidden):
+    return types.SimpleNamespace(cls_layers="12", cls_pool="cls", hidden_size=hidden,
+                                 classifier_dropout=0.0, hidden_dropout_prob=0.0,
+                                 similarity_measure=measure)
+
+
+def make_pairs(n, d, gen, quant=None):
+    """tanh-range embeddings; positives are noisy copies (SURVEY 8d synthetic recipe)."""
+    z = torch.randn(n, d, generator=gen)
+    labels = (torch.rand(n, generator=gen) < 0.5).long()
+    noise = torch.randn(n, d, generator=gen)
+    other = torch.randn(n, d, generator=gen)
+    x = torch.tanh(z)
+    y = torch.where(labels[:, None] == 1, torch.tanh(z + 0.25 * noise), torch.tanh(other))
+    if quant is not None:
+        x = x.to(quant).float()
+        y = y.to(quant).float()
+    return x, y, labels
+
+
+def ref_loss_module(loss_type, margin):
+    # constructors exactly as reference src/models/text.py:1400-1409
+    if loss_type == "cosine":
+        return torch.nn.CosineEmbeddingLoss(margin=margin)
+    if loss_type == "bce":
+        return torch.nn.BCEWithLogitsLoss()
+    if loss_type == "euclidean":
+        return rloss.EuclideanDistanceLoss()
+    if loss_type == "hinge":
+        return rloss.HingeLoss(margin=margin)
+    return torch.nn.CrossEntropyLoss()
+
+
+def ref_step(measure, loss_type, x, y, labels, margin):
+    head = base.VecSimClassificationHead(cfg(measure, x.shape[1]))
+    x = x.clone().requires_grad_(True)
+    y = y.clone().requires_grad_(True)
+    sim = head.similarity(x, y)                                   # base.py:77
+    if measure == "cosine":                                       # base.py:79-86
+        probs = (sim + 1) / 2
+    elif measure in ("l1", "l2"):
+        probs = torch.exp(-sim)
+    else:
+        probs = head.sigmoid(sim)
+    fct = ref_loss_module(loss_type, margin)
+    # ladder, text.py:1468-1477 (bce with labels.float(): the reference's long labels crash)
+    if loss_type == "cosine":
+        loss = fct(x, y, (labels * 2 - 1).view(-1))
+    elif loss_type in ("hinge", "euclidean"):
+        loss = fct(sim.view(-1), (labels * 2 - 1).view(-1))
+    else:
+        loss = fct(sim.view(-1), labels.view(-1).float())
+    loss.backward()
+    return [t.detach().numpy() for t in (sim, probs, loss, x.grad, y.grad)]
+
+
+def gen_pairs():
+    out = {}
+    gen = torch.Generator().manual_seed(1)
+    shapes = [("a", 33, 72, None), ("b", 16, 768, None), ("c", 40, 64, torch.bfloat16),
+              ("d", 5, 1024, torch.float16), ("e", 1, 8, None), ("f", 19, 50, None)]
+    combos = [(m, l) for m in ("inner_product", "cosine", "l1", "l2")
+              for l in ("bce", "hinge", "euclidean", "cosine")]
+    for tag, n, d, quant in shapes:
+        x, y, labels = make_pairs(n, d, gen, quant)
+        if tag == "a":     # edge rows: zero row, identical rows, tiny-norm row
+            x[0] = 0
+            y[1] = x[1]
+            x[2] = 1e-10
+            x[3] = 0
+            y[3] = 0
+        out[f"{tag}/x"], out[f"{tag}/y"], out[f"{tag}/labels"] = x.numpy(), y.numpy(), labels.numpy()
+        for m, l in combos:
+            for margin in ((1.0, 0.3) if l in ("hinge", "cosine") else (1.0,)):
+                if l == "euclidean" and m in ("inner_product", "cosine"):
+                    xs, ys = x, y            # s**-1 of signed scores is still defined; keep it
+                else:
+                    xs, ys = x, y
+                sim, probs, loss, dx, dy = ref_step(m, l, xs, ys, labels, margin)
+                key = f"{tag}/{m}/{l}/{margin}"
+                out[key + "/sim"], out[key + "/probs"], out[key + "/loss"] = sim, probs, loss
+                out[key + "/dx"], out[key + "/dy"] = dx, dy
+    np.savez_compressed(os.path.join(HERE, "pair_golden.npz"), **out)
+    print("pair_golden:", len(out), "arrays")
+
+
+def gen_heads():
+    out = {}
+    gen = torch.Generator().manual_seed(2)
+    for m in ("inner_product", "cosine", "l1", "l2"):
+        h = 48
+        head = base.VecSimClassificationHead(cfg(m, h)).eval()
+        with torch.no_grad():
+            head.dense.weight.copy_(torch.randn(h, h, generator=gen) * 0.2)
+            head.dense.bias.copy_(torch.randn(h, generator=gen) * 0.1)
+        f1 = torch.randn(21, h, generator=gen)
+        f2 = torch.randn(21, h, generator=gen)
+        with torch.no_grad():
+            x, y, sim, probs = head(f1, f2)                       # base.py:66-88
+        for k, v in dict(w=head.dense.weight, b=head.dense.bias, f1=f1, f2=f2, x=x, y=y, sim=sim,
+                         probs=probs).items():
+            out[f"vecsim/{m}/{k}"] = v.detach().numpy()
+    # TwoTowerClassificationHead + CE (cls / "softmax" measure)
+    for tag, n, h in (("s", 27, 40), ("m", 9, 768)):
+        head = base.TwoTowerClassificationHead(h).eval()
+        with torch.no_grad():
+            head.out_proj.weight.copy_(torch.randn(2, 2 * h, generator=gen) * 0.05)
+            head.out_proj.bias.copy_(torch.randn(2, generator=gen) * 0.05)
+        f1 = torch.tanh(torch.randn(n, h, generator=gen)).requires_grad_(True)
+        f2 = torch.tanh(torch.randn(n, h, generator=gen)).requires_grad_(True)
+        labels = (torch.rand(n, generator=gen) < 0.5).long()
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            x, y, logits, probs = head(f1, f2)                    # base.py:103-117
+        loss = torch.nn.CrossEntropyLoss()(logits.view(-1, 2), labels.view(-1))   # text.py:1473
+        loss.backward()
+        for k, v in dict(w=head.out_proj.weight, b=head.out_proj.bias, f1=f1, f2=f2, labels=labels,
+                         logits=logits, probs=probs, loss=loss, dx=f1.grad, dy=f2.grad,
+                         dw=head.out_proj.weight.grad, db=head.out_proj.bias.grad).items():
+            out[f"twotower/{tag}/{k}"] = v.detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "head_golden.npz"), **out)
+    print("head_golden:", len(out), "arrays")
+
+
+def gen_retrieval():
+    """All-pairs scores through the reference's PAIRWISE modules (expanded pairs), then a stable
+    sort: the definition of retrieval in SURVEY 1.  Entries are multiples of 1/2 in [-1,1] with
+    D=32 so every fp32 partial sum is exact (order independent) -> top-k indices are bit-exact
+    targets; duplicate catalog rows force ties."""
+    out = {}
+    gen = torch.Generator().manual_seed(3)
+    q_n, c_n, d, k = 12, 400, 32, 20
+    vals = torch.tensor([-1.0, -0.5, 0.0, 0.5, 1.0])
+    c = vals[torch.randint(0, 5, (c_n, d), generator=gen)]
+    c[100:140] = c[0:40]          # duplicates -> ties
+    c[399] = 0                    # zero row
+    q = c[torch.randint(0, c_n, (q_n,), generator=gen)].clone()
+    q[1] = vals[torch.randint(0, 5, (d,), generator=gen)]
+    out["q"], out["c"], out["k"] = q.numpy(), c.numpy(), np.int64(k)
+    qe = q[:, None, :].expand(q_n, c_n, d).reshape(-1, d)
+    ce = c[None, :, :].expand(q_n, c_n, d).reshape(-1, d)
+    for m in ("inner_product", "cosine", "l1", "l2"):
+        head = base.VecSimClassificationHead(cfg(m, d))
+        sc = head.similarity(qe, ce).reshape(q_n, c_n)
+        v, i = torch.sort(sc, dim=1, descending=m in ("inner_product", "cosine"), stable=True)
+        out[f"{m}/scores"], out[f"{m}/top_scores"], out[f"{m}/top_idx"] = \
+            sc.numpy(), v[:, :k].numpy(), i[:, :k].numpy()
+    np.savez_compressed(os.path.join(HERE, "retrieval_golden.npz"), **out)
+    print("retrieval_golden:", len(out), "arrays")
+
+
+def gen_submit():
+    out = {}
+    tgt0, thr = [], []
+    with open(os.path.join(REF, "submit", "deepAI_result.jsonl")) as f:
+        for line in f:
+            d = json.loads(line)
+            tgt0.append(json.loads(d["tgt_item_emb"])[0])
+            thr.append(float(d["threshold"]))
+    tgt0, thr = np.array(tgt0, dtype=np.float64), np.array(thr, dtype=np.float64)
+    out["deepai/tgt0"], out["deepai/threshold"] = tgt0, thr
+    out["deepai/labels"] = tgt0 >= thr          # compute() pass-through (similarity.py:27-28) >= threshold
+    print("deepAI rows", len(tgt0), "positives", int(out["deepai/labels"].sum()))
+    # commented weight sets of submit/similarity.py:5-18
+    src = open(os.path.join(REF, "submit", "similarity.py")).read()
+    names = re.findall(r"^# ([\w\-]+-ce)\s*$", src, flags=re.M)
+    ws = re.findall(r"^# w = np\.array\((.*)\)\s*$", src, flags=re.M)
+    bs = re.findall(r"^# b = np\.array\((.*)\)\s*$", src, flags=re.M)
+    assert len(names) == len(ws) == len(bs) == 4, (len(names), len(ws), len(bs))
+    gen = np.random.default_rng(4)
+    for i, (n, w, b) in enumerate(zip(names, ws, bs)):
+        w = np.array(json.loads(w))
+        b = np.array(json.loads(b))
+        h = w.shape[1] // 2
+        e1 = np.tanh(gen.standard_normal((6, h)))
+        e2 = np.tanh(gen.standard_normal((6, h)))
+        res = []
+        for a, c in zip(e1, e2):
+            # body of similarity.py:19-24
+            emb = np.array(list(a) + list(c))
+            logits = w.dot(emb) + b
+            el = np.exp(logits)
+            res.append((el / np.sum(el))[1])
+        out[f"softmax/{i}/w"], out[f"softmax/{i}/b"] = w, b
+        out[f"softmax/{i}/e1"], out[f"softmax/{i}/e2"], out[f"softmax/{i}/p1"] = e1, e2, np.array(res)
+        print("weights", n, w.shape)
+    np.savez_compressed(os.path.join(HERE, "submit_golden.npz"), **out)
+
+
+if __name__ == "__main__":
+    gen_pairs()
+    gen_heads()
+    gen_retrieval()
+    gen_submit()
