@@ -1,0 +1,158 @@
+/* ia_b200.h -- C ABI of the B200-native two-tower vector-similarity path.
+ *
+ * Drop-in boundary for the hot path of sunzeyeah/item-alignment (file:line below are into the
+ * reference tree).  The reference is pure Python/PyTorch, so "the reference's FFI for this path"
+ * is a ctypes binding: item_alignment_b200/_lib.py is that binding and INTEGRATION.md shows the
+ * stub a reference maintainer would add.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every entry point returns 0 (IA_OK) or a negative ia_status; ia_last_error() gives the
+ *     thread-local message.  Nothing here falls back to the CPU.
+ *   - device entry points are asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     allocate user-visible memory and never synchronise.  *_host entry points take HOST buffers,
+ *     own their staging/streams and return after the result is on the host.
+ *   - x, y are row-major [n, d] with leading dimensions ldx, ldy in ELEMENTS; sim/probs/loss are fp32.
+ *   - labels are int64 {0,1} exactly as the reference's collate functions produce them
+ *     (src/data/data.py:237); t = 2*label-1 is formed inside the kernels (src/models/text.py:1471,1475).
+ */
+#ifndef IA_B200_H
+#define IA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ia_stream_t; /* cudaStream_t */
+
+typedef enum {
+  IA_OK = 0,
+  IA_ERR_INVALID = -1,     /* bad argument (reference raises ValueError, src/models/base.py:64,86) */
+  IA_ERR_UNSUPPORTED = -2, /* dtype / shape not supported by the CUDA path */
+  IA_ERR_CUDA = -3,        /* CUDA runtime / driver error */
+  IA_ERR_WORKSPACE = -4    /* workspace too small */
+} ia_status;
+
+/* config.similarity_measure, src/models/base.py:54-62 */
+typedef enum { IA_INNER = 0, IA_COSINE = 1, IA_L1 = 2, IA_L2 = 3 } ia_measure;
+/* config.loss_type on a VecSim head, src/models/text.py:1400-1409 ("ce" belongs to the softmax head) */
+typedef enum { IA_LOSS_BCE = 0, IA_LOSS_HINGE = 1, IA_LOSS_EUCLIDEAN = 2, IA_LOSS_COSINE = 3 } ia_loss;
+typedef enum { IA_F32 = 0, IA_BF16 = 1, IA_F16 = 2 } ia_dtype;
+/* _Loss.reduction, src/models/loss.py:58-68,122-134 */
+typedef enum { IA_RED_NONE = 0, IA_RED_MEAN = 1, IA_RED_SUM = 2 } ia_reduction;
+
+const char* ia_version(void);
+const char* ia_last_error(void);
+/* Bytes of zero-initialised device scratch the *_fwd_bwd entry points need (deterministic two-stage
+ * loss reduction).  One workspace per concurrently used stream; kernels leave it zeroed. */
+size_t ia_workspace_bytes(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches evidence). */
+int64_t ia_launch_count(void);
+
+/* ---- pair scoring, forward only ------------------------------------------------------------
+ * Replaces: InnerProduct.forward (src/models/base.py:29-34), nn.CosineSimilarity / nn.PairwiseDistance
+ * as constructed at base.py:54-62, the probability map of VecSimClassificationHead.forward
+ * (base.py:79-86) and the threshold labelling `probs >= threshold` (finetune_text.py:576-580;
+ * the comparison is done in double like numpy does with an np.arange threshold).
+ * probs and labels_out may be NULL. */
+int ia_pair_score_fwd(int measure, int dtype, const void* x, const void* y, int64_t n, int64_t d,
+                      int64_t ldx, int64_t ldy, float* sim, float* probs, double threshold,
+                      uint8_t* labels_out, ia_stream_t stream);
+
+/* ---- fused score + loss, forward AND backward in one HBM pass --------------------------------
+ * Replaces, for one batch: the similarity + probs above, the loss ladder (src/models/text.py:1468-1477:
+ * bce -> nn.BCEWithLogitsLoss on sim; hinge -> HingeLoss, src/models/loss.py:126-134; euclidean ->
+ * EuclideanDistanceLoss, loss.py:61-68; cosine -> nn.CosineEmbeddingLoss on the embeddings) and the
+ * autograd backward of all of it (finetune_text.py:479-482).
+ *   loss_out  : 1 float (mean / sum) or n floats (IA_RED_NONE)
+ *   dx, dy    : [n, d] gradients in grad_dtype (= dtype, or IA_F32), leading dims lddx / lddy;
+ *               both NULL -> forward + loss only
+ *   grad_scale: upstream d(total)/d(loss) folded into dx, dy (1.0 for a plain loss.backward())
+ *   sim, probs may be NULL. */
+int ia_pair_score_loss_fwd_bwd(int measure, int loss, float margin, int reduction, int dtype,
+                               int grad_dtype, const void* x, const void* y, int64_t ldx, int64_t ldy,
+                               const int64_t* labels, int64_t n, int64_t d, float* sim, float* probs,
+                               float* loss_out, void* dx, void* dy, int64_t lddx, int64_t lddy,
+                               float grad_scale, void* workspace, size_t workspace_bytes,
+                               ia_stream_t stream);
+
+/* ---- backward of the score alone (upstream gradient is an arbitrary per-pair vector) ----------
+ * Replaces autograd of InnerProduct / CosineSimilarity / PairwiseDistance when the caller keeps the
+ * reference's unfused head -> loss module sequence.  gsim: [n] fp32 = dL/dsim. */
+int ia_pair_score_bwd(int measure, int dtype, int grad_dtype, const void* x, const void* y,
+                      int64_t ldx, int64_t ldy, const float* gsim, int64_t n, int64_t d, void* dx,
+                      void* dy, int64_t lddx, int64_t lddy, ia_stream_t stream);
+
+/* ---- elementwise losses on a score vector (the reference's loss modules on their own) ---------
+ * HingeLoss.forward (loss.py:126-134), EuclideanDistanceLoss.forward (loss.py:61-68), BCEWithLogits
+ * (text.py:1403).  target_pm1: int64 in {-1,+1} for hinge / euclidean, {0,1} for bce.
+ * loss_out: 1 float or n floats; gsim (may be NULL): d loss / d sim * grad_scale. */
+int ia_score_loss_fwd_bwd(int loss, float margin, int reduction, const float* sim,
+                          const int64_t* target, int64_t n, float* loss_out, float* gsim,
+                          float grad_scale, void* workspace, size_t workspace_bytes,
+                          ia_stream_t stream);
+
+/* ---- "softmax" measure: TwoTowerClassificationHead (base.py:103-117) + CrossEntropyLoss --------
+ * logits = [x ; y] . W^T + b with W [2, 2h] fp32 row-major, probs = softmax(logits) (numpy twin:
+ * submit/similarity.py:19-24).  labels NULL -> forward only.  With labels: loss (mean CE,
+ * text.py:1408-1409,1473) and, when non-NULL, dx, dy (grad_dtype), dW [2,2h], db [2] (fp32).
+ * workspace: ia_softmax_head_workspace_bytes(h). */
+size_t ia_softmax_head_workspace_bytes(int64_t h);
+int ia_softmax_head_fwd_bwd(int dtype, int grad_dtype, const void* x, const void* y, int64_t ldx,
+                            int64_t ldy, const float* w, const float* b, const int64_t* labels,
+                            int64_t n, int64_t h, float* logits, float* probs, float* loss_out,
+                            void* dx, void* dy, int64_t lddx, int64_t lddy, float* dw, float* db,
+                            float grad_scale, void* workspace, size_t workspace_bytes,
+                            ia_stream_t stream);
+
+/* ---- in-place scale of gradients by a device scalar (autograd upstream != 1, e.g. GradScaler) --
+ * No-op on the device when *g == 1.0f. */
+int ia_scale_inplace(int dtype, void* a, void* b, int64_t count, const float* g, ia_stream_t stream);
+
+/* ---- row inverse norms: 1 / max(||row||, eps) (cosine retrieval pre-pass, base.py:58 eps) ------ */
+int ia_row_inv_norm(int dtype, const void* x, int64_t n, int64_t d, int64_t ldx, float eps,
+                    float* out, ia_stream_t stream);
+
+/* ---- catalog retrieval: all-pairs score + per-query top-k --------------------------------------
+ * No reference implementation exists (README.md:12,16 motivate it); semantics = the pairwise
+ * similarity above for every (query, catalog row), top-k by a stable sort (ties -> lower index;
+ * nearest precedent torchkge/torchkge/inference.py:243-246).  Results are 64-bit keys
+ *   key = (orderable(score) << 32) | (0xFFFFFFFF - global_row)      (distances: score word complemented)
+ * so one unsigned max-compare means "better score, then lower index" in the kernel epilogue, the
+ * shard merge and after the NCCL all-gather alike.
+ *
+ * A catalog handle borrows the device catalog [c, d] (bf16 for the tensor-core measures; fp32/bf16
+ * for l1/l2) and owns inverse norms, TMA descriptors and scratch. */
+typedef struct ia_catalog ia_catalog;
+int ia_catalog_create(ia_catalog** out, int dtype, const void* catalog, int64_t c, int64_t d,
+                      int64_t ld, int64_t row_base, ia_stream_t stream);
+void ia_catalog_destroy(ia_catalog* cat);
+/* keys_out: [q, k] u64 sorted best-first.  k <= IA_MAX_K. */
+#define IA_MAX_K 128
+int ia_catalog_topk(ia_catalog* cat, int measure, const void* queries, int64_t q, int64_t ldq,
+                    int k, uint64_t* keys_out, ia_stream_t stream);
+/* bytes of device scratch ia_catalog_topk uses internally for (q, k) (allocated lazily, reused) */
+/* merge `parts` sorted key lists [parts, q, k] -> [q, k] (after the all-gather of shard results) */
+int ia_topk_merge(const uint64_t* keys_in, int parts, int64_t q, int k, uint64_t* keys_out,
+                  ia_stream_t stream);
+/* keys -> fp32 scores + int64 global rows */
+int ia_unpack_keys(const uint64_t* keys, int64_t count, int descending, float* scores,
+                   int64_t* rows, ia_stream_t stream);
+
+/* ---- host-buffer entry points (what a CPU-side caller of the reference binds) -------------------
+ * Same maths with HOST inputs/outputs: pinned or pageable host pointers, chunked H2D overlapped
+ * with the kernels on internal streams, result copied back; returns when the outputs are valid.
+ * Replaces the vectorised CPU scoring of finetune_text.py:566-580 and per-pair compute() loops
+ * (submit/similarity.py:27, pred_bert.py:47-52) for a whole batch. */
+int ia_pair_score_host(int measure, int dtype, const void* x, const void* y, int64_t n, int64_t d,
+                       float* sim, float* probs, double threshold, uint8_t* labels_out, int device);
+int ia_pair_score_loss_host(int measure, int loss, float margin, int reduction, int dtype,
+                            const void* x, const void* y, const int64_t* labels, int64_t n, int64_t d,
+                            float* loss_out, void* dx, void* dy, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IA_B200_H */

@@ -1,0 +1,21 @@
+"""item_alignment_b200 -- the two-tower vector-similarity hot path of sunzeyeah/item-alignment, rebuilt for
+B200 (sm_100a): hand-written CUDA kernels behind a C ABI (include/ia_b200.h, csrc/), a ctypes binding
+(_lib.py) and a host-side mirror of the reference's head / loss / compute() interface.
+
+Importing the package does not load the CUDA library; the first operator call does, and raises if it is
+missing (there is no CPU fallback).
+"""
+from . import functional
+from ._lib import IAError, launch_count
+from .heads import InnerProduct, PairSimilarity, TwoTowerClassificationHead, VecSimClassificationHead
+from .loss import EuclideanDistanceLoss, HingeLoss, apply_loss_ladder, build_loss_fct, two_tower_step
+from .retrieval import CatalogIndex, ShardedCatalogIndex, all_gather_keys, merge_keys, shard_bounds, unpack_keys
+from .similarity import compute, compute_many, configure
+
+__all__ = [
+    "functional", "IAError", "launch_count", "InnerProduct", "PairSimilarity", "TwoTowerClassificationHead",
+    "VecSimClassificationHead", "EuclideanDistanceLoss", "HingeLoss", "apply_loss_ladder", "build_loss_fct",
+    "two_tower_step", "CatalogIndex", "ShardedCatalogIndex", "all_gather_keys", "merge_keys", "shard_bounds", "unpack_keys",
+    "compute", "compute_many", "configure",
+]
+__version__ = "0.1.0"

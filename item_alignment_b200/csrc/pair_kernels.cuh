@@ -1,0 +1,358 @@
+// Pair scoring kernels: one warp owns one pair (row of x, row of y).
+//
+// HBM-bound design: each pair's x and y rows are read ONCE with 128-bit streaming loads
+// (all of a row's loads are issued before the first use so every lane keeps 2*VPL requests in flight),
+// kept in registers as raw vectors, reduced with warp shuffles (sum xy, sum x^2, sum y^2, sum |d| / d^2),
+// the per-pair scalar math (score -> probability -> loss -> dL/ds) runs redundantly in every lane, and
+// dx, dy are produced from the same registers and written once with 128-bit stores.
+// Algorithmic traffic: forward 2*D*e + 8 B/pair, fused forward+backward 4*D*e + 16 B/pair.
+#pragma once
+#include "common.cuh"
+
+namespace ia {
+
+enum PairMode { kModeFwd = 0, kModeFused = 1, kModeBwd = 2 };
+
+struct PairParams {
+  const void* x;
+  const void* y;
+  int64_t ldx, ldy;            // elements
+  const int64_t* labels;       // fused
+  const float* gsim;           // bwd
+  int64_t n;
+  int d;
+  float* sim;
+  float* probs;
+  uint8_t* labels_out;         // fwd
+  double threshold;            // fwd
+  float* loss_out;             // fused
+  void* dx;
+  void* dy;
+  int64_t lddx, lddy;
+  int loss;
+  float margin;
+  int reduction;
+  float grad_scale;            // upstream * (1/n for mean)
+  double loss_scale;           // 1/n for mean, 1 otherwise
+  void* workspace;
+};
+
+// Per-pair sums gathered in one sweep over the registers.
+struct RowSums {
+  float xy, xx, yy, dist;  // dist = sum |d| (l1) or sum d^2 (l2), d = x - y + eps
+};
+
+template <int MEASURE, bool NEED_COS>
+__device__ __forceinline__ void accumulate(const float* fx, const float* fy, int n, RowSums& s) {
+#pragma unroll
+  for (int j = 0; j < n; ++j) {
+    if (MEASURE == IA_INNER || MEASURE == IA_COSINE || NEED_COS) s.xy = fmaf(fx[j], fy[j], s.xy);
+    if (MEASURE == IA_COSINE || NEED_COS) {
+      s.xx = fmaf(fx[j], fx[j], s.xx);
+      s.yy = fmaf(fy[j], fy[j], s.yy);
+    }
+    if (MEASURE == IA_L1) s.dist += fabsf(fx[j] - fy[j] + kPdistEps);
+    if (MEASURE == IA_L2) {
+      const float dd = fx[j] - fy[j] + kPdistEps;
+      s.dist = fmaf(dd, dd, s.dist);
+    }
+  }
+}
+
+// Coefficients of the gradient:   inner / cosine / cosine-embedding:  dx = A*y - Bx*x,  dy = A*x - By*y
+//                                  l1: dx = A*sign(d), dy = -dx ;  l2: dx = A*d, dy = -dx
+struct GradCoef {
+  float A, Bx, By;
+};
+
+template <int MEASURE>
+__device__ __forceinline__ float score_from_sums(const RowSums& s, float& nx, float& ny) {
+  if (MEASURE == IA_INNER) return s.xy;
+  if (MEASURE == IA_COSINE) {
+    // nn.CosineSimilarity (base.py:58): each side divided by max(norm, eps)
+    nx = fmaxf(sqrtf(s.xx), kCosEps);
+    ny = fmaxf(sqrtf(s.yy), kCosEps);
+    return s.xy / (nx * ny);
+  }
+  if (MEASURE == IA_L1) return s.dist;
+  return sqrtf(s.dist);
+}
+
+template <int MEASURE>
+__device__ __forceinline__ GradCoef score_grad_coef(const RowSums& s, float sim, float nx, float ny, float g) {
+  GradCoef c{0.f, 0.f, 0.f};
+  if (MEASURE == IA_INNER) {
+    c.A = g;
+  } else if (MEASURE == IA_COSINE) {
+    // ATen: ds/dx = (yh - s * x/|x|) / max(|x|,eps), with x/|x| := 0 at |x| = 0
+    const float rx = sqrtf(s.xx), ry = sqrtf(s.yy);
+    c.A = g / (nx * ny);
+    c.Bx = rx > 0.f ? g * sim / (nx * rx) : 0.f;
+    c.By = ry > 0.f ? g * sim / (ny * ry) : 0.f;
+  } else if (MEASURE == IA_L1) {
+    c.A = g;
+  } else {
+    c.A = sim > 0.f ? g / sim : 0.f;
+  }
+  return c;
+}
+
+template <typename T, typename G, int MEASURE, int MODE, bool COSLOSS, int VPL>
+__global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
+  constexpr int E = VecTraits<T>::kElems;
+  constexpr bool kGradCosForm = COSLOSS || MEASURE == IA_INNER || MEASURE == IA_COSINE;
+  const int lane = threadIdx.x & 31;
+  const int warp_in_block = threadIdx.x >> 5;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int nvec = p.d / E;
+  float loss_acc = 0.f;
+
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_in_block; row < p.n; row += warps_total) {
+    const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + row * p.ldx);
+    const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + row * p.ldy);
+    uint4 xv[VPL], yv[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        xv[i] = ldg_stream(xr + v);
+        yv[i] = ldg_stream(yr + v);
+      } else {
+        xv[i] = make_uint4(0, 0, 0, 0);
+        yv[i] = make_uint4(0, 0, 0, 0);
+      }
+    }
+    int label = 0;
+    float gup = 0.f;
+    if (MODE == kModeFused) label = (int)(__ldg(p.labels + row) != 0);
+    if (MODE == kModeBwd) gup = __ldg(p.gsim + row);
+
+    RowSums s{0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      if (lane + 32 * i < nvec) {   // masked lanes must not add the l1/l2 eps
+        float fx[E], fy[E];
+        unpack<T>(xv[i], fx);
+        unpack<T>(yv[i], fy);
+        accumulate<MEASURE, COSLOSS>(fx, fy, E, s);
+      }
+    }
+    if (MEASURE == IA_INNER || MEASURE == IA_COSINE || COSLOSS) s.xy = warp_sum(s.xy);
+    if (MEASURE == IA_COSINE || COSLOSS) { s.xx = warp_sum(s.xx); s.yy = warp_sum(s.yy); }
+    if (MEASURE == IA_L1 || MEASURE == IA_L2) s.dist = warp_sum(s.dist);
+
+    float nx = 1.f, ny = 1.f;
+    const float sim = score_from_sums<MEASURE>(s, nx, ny);
+
+    if (MODE != kModeBwd && lane == 0) {
+      if (p.sim) p.sim[row] = sim;
+      const float pr = prob_of<MEASURE>(sim);
+      if (p.probs) p.probs[row] = pr;
+      if (MODE == kModeFwd && p.labels_out) p.labels_out[row] = (uint8_t)((double)pr >= p.threshold);
+    }
+    if (MODE == kModeFwd) continue;
+
+    GradCoef c;
+    if (MODE == kModeFused) {
+      float li, g;
+      if (COSLOSS) {
+        // nn.CosineEmbeddingLoss (text.py:1401,1471): c = xy / sqrt((xx+eps)(yy+eps))
+        const float a = s.xx + kCosEmbEps, b = s.yy + kCosEmbEps;
+        const float den = sqrtf(a * b);
+        const float cs = s.xy / den;
+        float gc;
+        if (label) { li = 1.f - cs; gc = -1.f; }
+        else { li = fmaxf(0.f, cs - p.margin); gc = (cs - p.margin) > 0.f ? 1.f : 0.f; }
+        gc *= p.grad_scale;
+        c.A = gc / den; c.Bx = gc * cs / a; c.By = gc * cs / b;
+      } else {
+        li = scalar_loss(p.loss, sim, label, p.margin, g);
+        c = score_grad_coef<MEASURE>(s, sim, nx, ny, g * p.grad_scale);
+      }
+      if (p.reduction == IA_RED_NONE) { if (lane == 0) p.loss_out[row] = li; }
+      else loss_acc += li;
+    } else {
+      c = score_grad_coef<MEASURE>(s, sim, nx, ny, gup);
+    }
+
+    if (p.dx != nullptr) {
+      G* dxr = static_cast<G*>(p.dx) + row * p.lddx;
+      G* dyr = static_cast<G*>(p.dy) + row * p.lddy;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) {
+          float fx[E], fy[E], gx[E], gy[E];
+          unpack<T>(xv[i], fx);
+          unpack<T>(yv[i], fy);
+#pragma unroll
+          for (int j = 0; j < E; ++j) {
+            if (kGradCosForm) {
+              gx[j] = c.A * fy[j] - c.Bx * fx[j];
+              gy[j] = c.A * fx[j] - c.By * fy[j];
+            } else if (MEASURE == IA_L1) {
+              const float dd = fx[j] - fy[j] + kPdistEps;
+              gx[j] = dd > 0.f ? c.A : (dd < 0.f ? -c.A : 0.f);
+              gy[j] = -gx[j];
+            } else {
+              const float dd = fx[j] - fy[j] + kPdistEps;
+              gx[j] = c.A * dd;
+              gy[j] = -gx[j];
+            }
+          }
+          Packer<G, E>::store(dxr + (int64_t)v * E, gx);
+          Packer<G, E>::store(dyr + (int64_t)v * E, gy);
+        }
+      }
+    }
+  }
+
+  if (MODE == kModeFused) {
+    if (p.reduction != IA_RED_NONE) {
+      __shared__ float warp_loss[8];
+      if (lane == 0) warp_loss[warp_in_block] = loss_acc;
+      __syncthreads();
+      double blk = 0.0;
+      if (threadIdx.x == 0) {
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) blk += (double)warp_loss[w];
+      }
+      grid_sum_finish(blk, p.workspace, p.loss_out, p.loss_scale);
+    }
+  }
+}
+
+// Any D, any alignment: scalar loads, two sweeps over the row (the second one hits L1/L2).
+template <typename T, typename G, int MEASURE, int MODE, bool COSLOSS>
+__global__ void __launch_bounds__(256) pair_kernel_generic(const PairParams p) {
+  constexpr bool kGradCosForm = COSLOSS || MEASURE == IA_INNER || MEASURE == IA_COSINE;
+  const int lane = threadIdx.x & 31;
+  const int warp_in_block = threadIdx.x >> 5;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float loss_acc = 0.f;
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_in_block; row < p.n; row += warps_total) {
+    const T* xr = static_cast<const T*>(p.x) + row * p.ldx;
+    const T* yr = static_cast<const T*>(p.y) + row * p.ldy;
+    RowSums s{0.f, 0.f, 0.f, 0.f};
+    for (int j = lane; j < p.d; j += 32) {
+      const float fx = to_float<T>(xr[j]), fy = to_float<T>(yr[j]);
+      accumulate<MEASURE, COSLOSS>(&fx, &fy, 1, s);
+    }
+    s.xy = warp_sum(s.xy); s.xx = warp_sum(s.xx); s.yy = warp_sum(s.yy); s.dist = warp_sum(s.dist);
+    float nx = 1.f, ny = 1.f;
+    const float sim = score_from_sums<MEASURE>(s, nx, ny);
+    if (MODE != kModeBwd && lane == 0) {
+      if (p.sim) p.sim[row] = sim;
+      const float pr = prob_of<MEASURE>(sim);
+      if (p.probs) p.probs[row] = pr;
+      if (MODE == kModeFwd && p.labels_out) p.labels_out[row] = (uint8_t)((double)pr >= p.threshold);
+    }
+    if (MODE == kModeFwd) continue;
+    GradCoef c;
+    if (MODE == kModeFused) {
+      const int label = (int)(__ldg(p.labels + row) != 0);
+      float li, g;
+      if (COSLOSS) {
+        const float a = s.xx + kCosEmbEps, b = s.yy + kCosEmbEps;
+        const float den = sqrtf(a * b);
+        const float cs = s.xy / den;
+        float gc;
+        if (label) { li = 1.f - cs; gc = -1.f; }
+        else { li = fmaxf(0.f, cs - p.margin); gc = (cs - p.margin) > 0.f ? 1.f : 0.f; }
+        gc *= p.grad_scale;
+        c.A = gc / den; c.Bx = gc * cs / a; c.By = gc * cs / b;
+      } else {
+        li = scalar_loss(p.loss, sim, label, p.margin, g);
+        c = score_grad_coef<MEASURE>(s, sim, nx, ny, g * p.grad_scale);
+      }
+      if (p.reduction == IA_RED_NONE) { if (lane == 0) p.loss_out[row] = li; }
+      else loss_acc += li;
+    } else {
+      c = score_grad_coef<MEASURE>(s, sim, nx, ny, __ldg(p.gsim + row));
+    }
+    if (p.dx != nullptr) {
+      G* dxr = static_cast<G*>(p.dx) + row * p.lddx;
+      G* dyr = static_cast<G*>(p.dy) + row * p.lddy;
+      for (int j = lane; j < p.d; j += 32) {
+        const float fx = to_float<T>(xr[j]), fy = to_float<T>(yr[j]);
+        float gx, gy;
+        if (kGradCosForm) {
+          gx = c.A * fy - c.Bx * fx;
+          gy = c.A * fx - c.By * fy;
+        } else if (MEASURE == IA_L1) {
+          const float dd = fx - fy + kPdistEps;
+          gx = dd > 0.f ? c.A : (dd < 0.f ? -c.A : 0.f);
+          gy = -gx;
+        } else {
+          gx = c.A * (fx - fy + kPdistEps);
+          gy = -gx;
+        }
+        dxr[j] = from_float<G>(gx);
+        dyr[j] = from_float<G>(gy);
+      }
+    }
+  }
+  if (MODE == kModeFused && p.reduction != IA_RED_NONE) {
+    __shared__ float warp_loss[8];
+    if (lane == 0) warp_loss[warp_in_block] = loss_acc;
+    __syncthreads();
+    double blk = 0.0;
+    if (threadIdx.x == 0)
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) blk += (double)warp_loss[w];
+    grid_sum_finish(blk, p.workspace, p.loss_out, p.loss_scale);
+  }
+}
+
+// ---------------------------------------------------------------------------------- launch
+template <void (*kernel)(const PairParams)>
+int launch_rows(const PairParams& p, cudaStream_t stream) {
+  constexpr int kThreads = 256, kWarps = 8;
+  static int cached_bps = 0;   // one instantiation per kernel -> per-kernel occupancy cache
+  if (cached_bps == 0) cached_bps = blocks_per_sm(kernel, kThreads);
+  int64_t want = (p.n + kWarps - 1) / kWarps;
+  int64_t cap = (int64_t)sm_count() * cached_bps;
+  if (cap > kMaxPartials) cap = kMaxPartials;
+  int grid = (int)(want < cap ? want : cap);
+  if (grid < 1) grid = 1;
+  kernel<<<grid, kThreads, 0, stream>>>(p);
+  IA_LAUNCH_CHECK();
+  return IA_OK;
+}
+
+template <typename T, typename G, int MEASURE, int MODE, bool COSLOSS>
+int launch_pair_vpl(const PairParams& p, bool vec_ok, cudaStream_t stream) {
+  constexpr int E = VecTraits<T>::kElems;
+  const int nvec = p.d / E;
+  if (!vec_ok || nvec > 32 * 8) return launch_rows<pair_kernel_generic<T, G, MEASURE, MODE, COSLOSS>>(p, stream);
+  if (nvec <= 64) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2>>(p, stream);
+  if (nvec <= 128) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4>>(p, stream);
+  return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8>>(p, stream);
+}
+
+template <typename T, typename G, int MODE, bool COSLOSS>
+int launch_pair_measure(int measure, const PairParams& p, bool vec_ok, cudaStream_t stream) {
+  switch (measure) {
+    case IA_INNER: return launch_pair_vpl<T, G, IA_INNER, MODE, COSLOSS>(p, vec_ok, stream);
+    case IA_COSINE: return launch_pair_vpl<T, G, IA_COSINE, MODE, COSLOSS>(p, vec_ok, stream);
+    case IA_L1: return launch_pair_vpl<T, G, IA_L1, MODE, COSLOSS>(p, vec_ok, stream);
+    case IA_L2: return launch_pair_vpl<T, G, IA_L2, MODE, COSLOSS>(p, vec_ok, stream);
+  }
+  set_error("Unsupported similarty measure: %d", measure);
+  return IA_ERR_INVALID;
+}
+
+// one entry per (T, G): implemented in pair_<dtype>.cu
+template <typename T, typename G>
+int launch_pair(int mode, bool cosloss, int measure, const PairParams& p, bool vec_ok, cudaStream_t stream) {
+  if (mode == kModeFwd) return launch_pair_measure<T, G, kModeFwd, false>(measure, p, vec_ok, stream);
+  if (mode == kModeBwd) return launch_pair_measure<T, G, kModeBwd, false>(measure, p, vec_ok, stream);
+  if (cosloss) return launch_pair_measure<T, G, kModeFused, true>(measure, p, vec_ok, stream);
+  return launch_pair_measure<T, G, kModeFused, false>(measure, p, vec_ok, stream);
+}
+
+int launch_pair_f32_f32(int mode, bool cosloss, int measure, const PairParams& p, bool vec_ok, cudaStream_t s);
+int launch_pair_bf16_bf16(int mode, bool cosloss, int measure, const PairParams& p, bool vec_ok, cudaStream_t s);
+int launch_pair_bf16_f32(int mode, bool cosloss, int measure, const PairParams& p, bool vec_ok, cudaStream_t s);
+int launch_pair_f16_f16(int mode, bool cosloss, int measure, const PairParams& p, bool vec_ok, cudaStream_t s);
+int launch_pair_f16_f32(int mode, bool cosloss, int measure, const PairParams& p, bool vec_ok, cudaStream_t s);
+
+}  // namespace ia

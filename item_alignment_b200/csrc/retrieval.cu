@@ -1,0 +1,640 @@
+// Catalog retrieval: all-pairs scores + per-query top-k (see include/ia_b200.h for the semantics).
+//
+//  * inner / cosine on bf16|fp16 catalogs: a genuine dense contraction -> tcgen05 tensor cores.
+//    Persistent, warp-specialised CTAs: warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle),
+//    warp 1 = single-thread tcgen05.mma issuer (M=128 queries x N=256 catalog rows, K=16 per MMA, fp32
+//    accumulators double-buffered in the 512 TMEM columns), warps 2-5 = epilogue: tcgen05.ld the
+//    accumulator rows (one query per thread), fused normalise (x 1/|c| x 1/|q|), threshold filter against
+//    the running k-th best and a rare-path append/merge into the per-query sorted key list.  The Q x C
+//    score matrix is never materialised.
+//  * l1 / l2 (no MMA form because of |.|) and fp32 inputs: shared-memory-tiled CUDA-core kernel with the
+//    same top-k epilogue.
+//  * a CTA owns (query tile, catalog split); split results are merged by a small kernel.  All CTAs working
+//    on the same queries share their k-th best through tau_global so thresholds tighten across splits.
+#include <cuda.h>
+
+#include <mutex>
+#include <new>
+
+#include "retrieval.cuh"
+
+namespace ia {
+
+struct RetrParams {
+  int q_rows;
+  int64_t c_rows;
+  int d;
+  int k;
+  int n_qt;             // query tiles
+  int n_splits;         // catalog splits
+  int tiles_per_split;  // catalog tiles per split
+  int n_tiles;          // catalog tiles in total
+  int kblocks;          // K blocks of 64 (tensor-core kernel)
+  const float* cinv;    // [c_rows] 1/max(|c|,eps)   (cosine)
+  const float* qinv;    // [q_rows]                  (cosine)
+  uint64_t* lists;      // [n_splits*n_qt][BM][kListCap]
+  uint32_t* tau_global; // [n_qt*BM] best published k-th goodness per query (0 = none)
+  uint32_t row_base;    // global row id of catalog row 0 (shard offset)
+};
+
+// =============================================================================== tensor-core kernel
+namespace tc {
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int THREADS = 192;
+constexpr int BUF_BYTES = BM * kBufPitch * 8;
+constexpr int CINV_BYTES = 2 * BN * 4;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BUF_BYTES + CINV_BYTES + 256 + 1024;  // + barriers + align slack
+}  // namespace tc
+
+template <bool COSINE, int AB_FORMAT>
+__global__ void __launch_bounds__(tc::THREADS, 1)
+retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
+                   const RetrParams p) {
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* buf = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  float* cinv_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BUF_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + BUF_BYTES + CINV_BYTES);
+  uint64_t* full_bar = bars;                // [STAGES] TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;      // [STAGES] MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * STAGES;  // [2] MMA -> epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;     // [2] epilogue -> MMA
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_c);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int n_items = p.n_qt * p.n_splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int qt = item % p.n_qt, split = item / p.n_qt;
+        const int t0 = split * p.tiles_per_split;
+        const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+        for (int t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+            uint8_t* a_s = smem + stage * STAGE_BYTES;
+            tma_load_2d(a_s, &tmap_q, &full_bar[stage], kb * BK, qt * BM);
+            tma_load_2d(a_s + A_BYTES, &tmap_c, &full_bar[stage], kb * BK, t * BN);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(BM, BN, AB_FORMAT);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int split = item / p.n_qt;
+        const int t0 = split * p.tiles_per_split;
+        const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+            const uint64_t a_desc = umma_smem_desc_sw128(a_addr);
+            const uint64_t b_desc = umma_smem_desc_sw128(a_addr + A_BYTES);
+#pragma unroll
+            for (int k4 = 0; k4 < BK / 16; ++k4)   // +32 B (>>4 = 2) per K=16 step inside the swizzle atom
+              umma_f16(d_tmem, a_desc + 2 * k4, b_desc + 2 * k4, idesc, (kb | k4) != 0);
+            umma_commit(&empty_bar[stage]);          // smem slot free once these MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tfull_bar[acc]);              // accumulator complete
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: fused normalise + top-k
+    const int e = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row_local = e * 32 + lane;    // query row inside the tile == TMEM lane
+    const int etid = (warp - 2) * 32 + lane;  // 0..127 among epilogue threads
+    uint64_t* buf_warp = buf + (size_t)(e * 32) * kBufPitch;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int qt = item % p.n_qt, split = item / p.n_qt;
+      const int t0 = split * p.tiles_per_split;
+      const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+      const int q_row = qt * BM + row_local;
+      const bool q_ok = q_row < p.q_rows;
+      float qinv = 1.f;
+      if (COSINE) qinv = q_ok ? __ldg(p.qinv + q_row) : 0.f;
+      uint64_t* lists_warp = p.lists + ((size_t)item * BM + e * 32) * kListCap;
+      for (int i = lane; i < 32 * kListCap; i += 32) lists_warp[i] = 0ull;
+      __syncwarp();
+      uint32_t* tau_warp = p.tau_global + qt * BM + e * 32;
+      TopKThread st{0ull, 0};
+
+      for (int t = t0; t < t1; ++t) {
+        const int64_t j0 = (int64_t)t * BN;
+        float* cs = cinv_s + acc * BN;
+        if (COSINE) {
+          for (int i = etid; i < BN; i += 128) cs[i] = (j0 + i < p.c_rows) ? __ldg(p.cinv + j0 + i) : 0.f;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        {  // pick up what other CTAs have published for this query
+          const uint64_t gk = (uint64_t)(*reinterpret_cast<volatile uint32_t*>(tau_warp + lane)) << 32;
+          if (gk > st.thr_key) st.thr_key = gk;
+        }
+        float thr_f = st.thr_key ? score_of_goodness<true>((uint32_t)(st.thr_key >> 32)) : -INFINITY;
+
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + acc * BN;
+#pragma unroll 1
+        for (int g = 0; g < BN / 32; ++g) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + g * 32, r);
+          tmem_ld_wait();
+          float m = -INFINITY;
+          const float4* cs4 = reinterpret_cast<const float4*>(cs + g * 32);
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            float v0 = __uint_as_float(r[4 * c4 + 0]), v1 = __uint_as_float(r[4 * c4 + 1]);
+            float v2 = __uint_as_float(r[4 * c4 + 2]), v3 = __uint_as_float(r[4 * c4 + 3]);
+            if (COSINE) {
+              const float4 ci = cs4[c4];
+              v0 *= ci.x; v1 *= ci.y; v2 *= ci.z; v3 *= ci.w;
+            }
+            m = fmaxf(fmaxf(m, v0), fmaxf(v1, fmaxf(v2, v3)));
+          }
+          if (COSINE) m *= qinv;
+          if (__any_sync(kFull, q_ok && m >= thr_f)) {
+            // rare path: re-read this group's 32 columns one at a time and append the survivors
+#pragma unroll 1
+            for (int c = 0; c < 32; ++c) {
+              float s = __uint_as_float(tmem_ld_1(taddr + g * 32 + c));
+              tmem_ld_wait();
+              if (COSINE) s = (s * cs[g * 32 + c]) * qinv;
+              const int64_t j = j0 + g * 32 + c;
+              if (q_ok && j < p.c_rows && s >= thr_f) {
+                const uint64_t key = make_key<true>(s, p.row_base + (uint32_t)j);
+                if (key > st.thr_key) {
+                  buf_warp[lane * kBufPitch + st.cnt] = key;
+                  st.cnt++;
+                }
+              }
+              if (__any_sync(kFull, st.cnt == kBufSlots)) {
+                __syncwarp();
+                warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp);
+                thr_f = st.thr_key ? score_of_goodness<true>((uint32_t)(st.thr_key >> 32)) : -INFINITY;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      __syncwarp();
+      warp_compact(st, 1, p.k, buf_warp, lists_warp, tau_warp);   // flush
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =============================================================================== CUDA-core kernel
+namespace simt {
+constexpr int BM = 64, BN = 128, BK = 32, THREADS = 256;
+constexpr int QS = BK * (BM + 1), CS = BK * (BN + 1), SS = BM * (BN + 1);
+constexpr int STAGE_FLOATS = (QS + CS) > SS ? (QS + CS) : SS;
+constexpr int SMEM_BYTES = STAGE_FLOATS * 4 + BM * kBufPitch * 8;
+}  // namespace simt
+
+template <typename T, int MEASURE>
+__global__ void __launch_bounds__(simt::THREADS)
+retrieve_simt_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ cat, int64_t ldc, const RetrParams p) {
+  using namespace simt;
+  constexpr bool DESC = (MEASURE == IA_INNER || MEASURE == IA_COSINE);
+  constexpr bool DIST = !DESC;
+  extern __shared__ uint8_t smem_raw[];
+  float* Qs = reinterpret_cast<float*>(smem_raw);   // [BK][BM+1]
+  float* Cs = Qs + QS;                              // [BK][BN+1]
+  float* Ss = reinterpret_cast<float*>(smem_raw);   // [BM][BN+1] (aliases the staging tiles)
+  uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw + STAGE_FLOATS * 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int n_items = p.n_qt * p.n_splits;
+
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int qt = item % p.n_qt, split = item / p.n_qt;
+    const int t0 = split * p.tiles_per_split;
+    const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+    const int q0 = qt * BM;
+    // top-k state: threads 0..63 own one query each (warps 0 and 1)
+    TopKThread st{0ull, 0};
+    uint64_t* lists_warp = p.lists + ((size_t)item * BM + warp * 32) * kListCap;
+    uint64_t* buf_warp = buf + (size_t)(warp * 32) * kBufPitch;
+    uint32_t* tau_warp = p.tau_global + qt * BM + warp * 32;
+    float qinv = 1.f;
+    if (warp < 2) {
+      for (int i = lane; i < 32 * kListCap; i += 32) lists_warp[i] = 0ull;
+      if (MEASURE == IA_COSINE) qinv = (q0 + tid < p.q_rows) ? __ldg(p.qinv + q0 + tid) : 0.f;
+      __syncwarp();
+    }
+
+    for (int t = t0; t < t1; ++t) {
+      const int64_t j0 = (int64_t)t * BN;
+      float acc[4][8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+      for (int k0 = 0; k0 < p.d; k0 += BK) {
+        __syncthreads();   // previous tile's scan / previous k-block's compute done
+        for (int idx = tid; idx < BM * BK; idx += THREADS) {
+          const int row = idx / BK, kk = idx % BK;
+          float v = 0.f;
+          if (q0 + row < p.q_rows && k0 + kk < p.d) v = to_float<T>(q[(int64_t)(q0 + row) * ldq + k0 + kk]);
+          Qs[kk * (BM + 1) + row] = v;
+        }
+        for (int idx = tid; idx < BN * BK; idx += THREADS) {
+          const int row = idx / BK, kk = idx % BK;
+          // padded k / rows: c = eps so that (0 - eps) + eps == 0 adds nothing to an l1/l2 distance
+          float v = DIST ? kPdistEps : 0.f;
+          if (j0 + row < p.c_rows && k0 + kk < p.d) v = to_float<T>(cat[(j0 + row) * ldc + k0 + kk]);
+          Cs[kk * (BN + 1) + row] = v;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < BK; ++kk) {
+          float a[4], b[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[i] = Qs[kk * (BM + 1) + ty + 16 * i];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) b[j] = Cs[kk * (BN + 1) + tx + 16 * j];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (DESC) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+              else {
+                const float dd = a[i] - b[j] + kPdistEps;   // nn.PairwiseDistance: eps added to the difference
+                if (MEASURE == IA_L1) acc[i][j] += fabsf(dd);
+                else acc[i][j] = fmaf(dd, dd, acc[i][j]);
+              }
+            }
+        }
+      }
+      __syncthreads();   // all warps done with Qs/Cs before Ss (alias) is written
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) Ss[(ty + 16 * i) * (BN + 1) + tx + 16 * j] = acc[i][j];
+      __syncthreads();
+
+      if (warp < 2) {
+        const bool q_ok = q0 + tid < p.q_rows;
+        {
+          const uint64_t gk = (uint64_t)(*reinterpret_cast<volatile uint32_t*>(tau_warp + lane)) << 32;
+          if (gk > st.thr_key) st.thr_key = gk;
+        }
+        float thr_f = st.thr_key ? score_of_goodness<DESC>((uint32_t)(st.thr_key >> 32)) : (DESC ? -INFINITY : INFINITY);
+#pragma unroll 1
+        for (int c = 0; c < BN; ++c) {
+          float s = Ss[tid * (BN + 1) + c];
+          const int64_t j = j0 + c;
+          if (MEASURE == IA_L2) s = sqrtf(s);
+          if (MEASURE == IA_COSINE) s = (s * ((j < p.c_rows) ? __ldg(p.cinv + j) : 0.f)) * qinv;
+          const bool pass = DESC ? (s >= thr_f) : (s <= thr_f);
+          if (q_ok && j < p.c_rows && pass) {
+            const uint64_t key = make_key<DESC>(s, p.row_base + (uint32_t)j);
+            if (key > st.thr_key) {
+              buf_warp[lane * kBufPitch + st.cnt] = key;
+              st.cnt++;
+            }
+          }
+          if (__any_sync(kFull, st.cnt == kBufSlots)) {
+            __syncwarp();
+            warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp);
+            thr_f = st.thr_key ? score_of_goodness<DESC>((uint32_t)(st.thr_key >> 32)) : (DESC ? -INFINITY : INFINITY);
+          }
+        }
+      }
+    }
+    if (warp < 2) {
+      __syncwarp();
+      warp_compact(st, 1, p.k, buf_warp, lists_warp, tau_warp);
+    }
+  }
+}
+
+// =============================================================================== merge / unpack
+// One warp per query: merge `parts` sorted key lists into the best k.
+//   internal layout (tile_rows > 0): list of (part, q) at src + ((part*n_qt + q/tile_rows)*tile_rows + q%tile_rows)*kListCap
+//   flat layout     (tile_rows == 0): src + (part*q_rows + q)*src_len
+__global__ void __launch_bounds__(256) merge_lists_kernel(const uint64_t* __restrict__ src, int parts, int64_t q_rows,
+                                                          int n_qt, int tile_rows, int src_len, int k,
+                                                          uint64_t* __restrict__ out) {
+  __shared__ uint64_t work[8][kListCap];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* list = work[warp];
+  for (int64_t q = (int64_t)blockIdx.x * 8 + warp; q < q_rows; q += (int64_t)gridDim.x * 8) {
+    for (int i = lane; i < kListCap; i += 32) list[i] = 0ull;
+    __syncwarp();
+    uint64_t kth = 0;
+    for (int part = 0; part < parts; ++part) {
+      const uint64_t* s = tile_rows > 0
+          ? src + (((size_t)part * n_qt + (size_t)(q / tile_rows)) * tile_rows + (size_t)(q % tile_rows)) * kListCap
+          : src + ((size_t)part * q_rows + (size_t)q) * src_len;
+      for (int b = 0; b < src_len; b += 32) {
+        const uint64_t bk = (b + lane < src_len) ? s[b + lane] : 0ull;
+        // sorted descending: once the batch's best key cannot enter the list, the rest of this part cannot either
+        const uint64_t head = __shfl_sync(kFull, bk, 0);
+        if (head == 0 || (kth != 0 && head < kth)) break;
+        uint64_t Lr[4];
+        warp_load_list(Lr, list);
+        __syncwarp();
+        kth = warp_merge_keys(Lr, bk, k, list);
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < k; i += 32) out[(size_t)q * k + i] = list[i];
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256) unpack_keys_kernel(const uint64_t* __restrict__ keys, int64_t count, int descending,
+                                                          float* __restrict__ scores, int64_t* __restrict__ rows) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t key = keys[i];
+    if (key == 0) {   // fewer than k candidates
+      if (scores) scores[i] = descending ? -INFINITY : INFINITY;
+      if (rows) rows[i] = -1;
+      continue;
+    }
+    const uint32_t g = (uint32_t)(key >> 32);
+    if (scores) scores[i] = descending ? score_of_goodness<true>(g) : score_of_goodness<false>(g);
+    if (rows) rows[i] = (int64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFu));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) inv_norm_rows_kernel(const T* x, int64_t n, int d, int64_t ldx, float eps, float* out) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < n; row += (int64_t)gridDim.x * 8) {
+    const T* xr = x + row * ldx;
+    float a = 0.f;
+    for (int j = lane; j < d; j += 32) { const float v = to_float<T>(xr[j]); a = fmaf(v, v, a); }
+    a = warp_sum(a);
+    if (lane == 0) out[row] = 1.0f / fmaxf(sqrtf(a), eps);
+  }
+}
+
+// =============================================================================== host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// 2-D row-major [rows, d] 16-bit matrix, box = 64 columns (128 B, swizzle 128B) x box_rows rows
+static int make_tmap(CUtensorMap* map, int dtype, const void* base, int64_t rows, int64_t d, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) { set_error("cuTensorMapEncodeTiled not available from the driver"); return IA_ERR_CUDA; }
+  const cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = dtype == IA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return IA_ERR_CUDA; }
+  return IA_OK;
+}
+
+}  // namespace ia
+
+using namespace ia;
+
+struct ia_catalog {
+  int dtype;
+  const void* data;
+  int64_t c, d, ld;
+  uint32_t row_base;
+  int device;
+  float* cinv;          // [c]
+  bool tc_ok;           // tensor-core path usable (16-bit dtype, TMA-compatible layout)
+  CUtensorMap tmap_c;
+  // lazily grown scratch
+  uint64_t* lists; size_t lists_bytes;
+  uint32_t* tau; size_t tau_bytes;
+  float* qinv; size_t qinv_bytes;
+};
+
+static int grow(void** ptr, size_t* have, size_t need) {
+  if (*have >= need) return IA_OK;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr; *have = 0;
+  IA_CUDA_CHECK(cudaMalloc(ptr, need));
+  *have = need;
+  return IA_OK;
+}
+
+// choose the number of catalog splits: fill the SMs in whole waves, keep splits long enough to amortise warm-up
+static void plan_splits(int n_qt, int n_tiles, int ctas, int min_tiles, int* n_splits, int* tiles_per_split) {
+  int best_s = 1;
+  double best_eff = -1.0;
+  const int max_s = n_tiles / min_tiles > 1 ? n_tiles / min_tiles : 1;
+  for (int s = 1; s <= max_s && s <= 256; ++s) {
+    const int tps = (n_tiles + s - 1) / s;
+    const int real_s = (n_tiles + tps - 1) / tps;
+    const int64_t items = (int64_t)n_qt * real_s;
+    const int64_t waves = (items + ctas - 1) / ctas;
+    // time ~ waves * tps ; ideal ~ n_qt * n_tiles / ctas
+    const double eff = ((double)n_qt * n_tiles / ctas) / ((double)waves * tps);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best_s = real_s; }
+  }
+  *n_splits = best_s;
+  *tiles_per_split = (n_tiles + best_s - 1) / best_s;
+  *n_splits = (n_tiles + *tiles_per_split - 1) / *tiles_per_split;
+}
+
+extern "C" {
+
+int ia_catalog_create(ia_catalog** out, int dtype, const void* catalog, int64_t c, int64_t d, int64_t ld,
+                      int64_t row_base, ia_stream_t stream) {
+  if (out == nullptr || catalog == nullptr || c <= 0 || d <= 0 || ld < d || row_base < 0 ||
+      row_base + c > 0xFFFFFFFFll) {
+    set_error("bad catalog arguments (rows must fit 32-bit global ids)");
+    return IA_ERR_INVALID;
+  }
+  if (dtype < IA_F32 || dtype > IA_F16) { set_error("unsupported dtype %d", dtype); return IA_ERR_UNSUPPORTED; }
+  ia_catalog* cat = new (std::nothrow) ia_catalog();
+  if (!cat) { set_error("out of host memory"); return IA_ERR_CUDA; }
+  cat->dtype = dtype; cat->data = catalog; cat->c = c; cat->d = d; cat->ld = ld; cat->row_base = (uint32_t)row_base;
+  cat->lists = nullptr; cat->lists_bytes = 0; cat->tau = nullptr; cat->tau_bytes = 0; cat->qinv = nullptr; cat->qinv_bytes = 0;
+  cat->cinv = nullptr; cat->tc_ok = false;
+  cudaGetDevice(&cat->device);
+  cudaError_t e = cudaMalloc(&cat->cinv, sizeof(float) * (size_t)c);
+  if (e != cudaSuccess) { set_error("cudaMalloc(cinv) failed: %s", cudaGetErrorString(e)); delete cat; return IA_ERR_CUDA; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t want = (c + 7) / 8;
+  const int grid = (int)(want < 8 * sm_count() ? want : 8 * sm_count());
+  if (dtype == IA_F32) inv_norm_rows_kernel<float><<<grid, 256, 0, s>>>((const float*)catalog, c, (int)d, ld, kCosEps, cat->cinv);
+  else if (dtype == IA_BF16) inv_norm_rows_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)catalog, c, (int)d, ld, kCosEps, cat->cinv);
+  else inv_norm_rows_kernel<__half><<<grid, 256, 0, s>>>((const __half*)catalog, c, (int)d, ld, kCosEps, cat->cinv);
+  g_launches.fetch_add(1);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("inverse-norm launch failed: %s", cudaGetErrorString(e)); cudaFree(cat->cinv); delete cat; return IA_ERR_CUDA; }
+  if (dtype != IA_F32 && d % 8 == 0 && ld % 8 == 0 && reinterpret_cast<uintptr_t>(catalog) % 16 == 0) {
+    if (make_tmap(&cat->tmap_c, dtype, catalog, c, d, ld, tc::BN) == IA_OK) cat->tc_ok = true;
+  }
+  *out = cat;
+  return IA_OK;
+}
+
+void ia_catalog_destroy(ia_catalog* cat) {
+  if (!cat) return;
+  if (cat->cinv) cudaFree(cat->cinv);
+  if (cat->lists) cudaFree(cat->lists);
+  if (cat->tau) cudaFree(cat->tau);
+  if (cat->qinv) cudaFree(cat->qinv);
+  delete cat;
+}
+
+int ia_catalog_topk(ia_catalog* cat, int measure, const void* queries, int64_t q, int64_t ldq, int k,
+                    uint64_t* keys_out, ia_stream_t stream) {
+  if (cat == nullptr || queries == nullptr || keys_out == nullptr || q < 0 || ldq < cat->d) { set_error("bad arguments"); return IA_ERR_INVALID; }
+  if (measure < IA_INNER || measure > IA_L2) { set_error("Unsupported similarty measure: %d", measure); return IA_ERR_INVALID; }
+  if (k < 1 || k > IA_MAX_K) { set_error("k must be in [1, %d]", IA_MAX_K); return IA_ERR_INVALID; }
+  if (q == 0) return IA_OK;
+  if (q > 0x7FFFFFFF) { set_error("too many queries in one call"); return IA_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool desc = (measure == IA_INNER || measure == IA_COSINE);
+  bool use_tc = desc && cat->tc_ok && ldq % 8 == 0 && reinterpret_cast<uintptr_t>(queries) % 16 == 0;
+  CUtensorMap tmap_q;
+  if (use_tc && make_tmap(&tmap_q, cat->dtype, queries, q, cat->d, ldq, tc::BM) != IA_OK) use_tc = false;   // -> CUDA-core path
+  const int BM = use_tc ? tc::BM : simt::BM, BN = use_tc ? tc::BN : simt::BN;
+
+  RetrParams p{};
+  p.q_rows = (int)q; p.c_rows = cat->c; p.d = (int)cat->d; p.k = k;
+  p.n_qt = (int)((q + BM - 1) / BM);
+  p.n_tiles = (int)((cat->c + BN - 1) / BN);
+  p.kblocks = (int)((cat->d + tc::BK - 1) / tc::BK);
+  p.row_base = cat->row_base;
+  const int sms = sm_count();
+  int ctas = sms;
+  if (!use_tc) ctas = sms * 2;
+  plan_splits(p.n_qt, p.n_tiles, ctas, use_tc ? 8 : 4, &p.n_splits, &p.tiles_per_split);
+  const int64_t n_items = (int64_t)p.n_qt * p.n_splits;
+
+  int rc;
+  if ((rc = grow((void**)&cat->lists, &cat->lists_bytes, sizeof(uint64_t) * (size_t)n_items * BM * kListCap)) != IA_OK) return rc;
+  if ((rc = grow((void**)&cat->tau, &cat->tau_bytes, sizeof(uint32_t) * (size_t)p.n_qt * BM)) != IA_OK) return rc;
+  IA_CUDA_CHECK(cudaMemsetAsync(cat->tau, 0, sizeof(uint32_t) * (size_t)p.n_qt * BM, s));
+  p.lists = cat->lists; p.tau_global = cat->tau; p.cinv = cat->cinv;
+  if (measure == IA_COSINE) {
+    if ((rc = grow((void**)&cat->qinv, &cat->qinv_bytes, sizeof(float) * (size_t)q)) != IA_OK) return rc;
+    if ((rc = ia_row_inv_norm(cat->dtype, queries, q, cat->d, ldq, kCosEps, cat->qinv, stream)) != IA_OK) return rc;
+    p.qinv = cat->qinv;
+  }
+  const int grid = (int)(n_items < ctas ? n_items : ctas);
+
+  if (use_tc) {
+    const int fmt_bf16 = cat->dtype == IA_BF16;
+    auto launch = [&](auto kernel) -> int {
+      IA_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+      kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(tmap_q, cat->tmap_c, p);
+      IA_LAUNCH_CHECK();
+      return IA_OK;
+    };
+    if (measure == IA_COSINE) rc = fmt_bf16 ? launch(retrieve_tc_kernel<true, 1>) : launch(retrieve_tc_kernel<true, 0>);
+    else rc = fmt_bf16 ? launch(retrieve_tc_kernel<false, 1>) : launch(retrieve_tc_kernel<false, 0>);
+    if (rc != IA_OK) return rc;
+  } else {
+    auto launch = [&](auto kernel, auto* tq) -> int {
+      using TP = decltype(tq);
+      IA_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, simt::SMEM_BYTES));
+      kernel<<<grid, simt::THREADS, simt::SMEM_BYTES, s>>>((TP)queries, ldq, (TP)cat->data, cat->ld, p);
+      IA_LAUNCH_CHECK();
+      return IA_OK;
+    };
+#define IA_SIMT_DISPATCH(T)                                                                         \
+    switch (measure) {                                                                              \
+      case IA_INNER: rc = launch(retrieve_simt_kernel<T, IA_INNER>, (const T*)nullptr); break;      \
+      case IA_COSINE: rc = launch(retrieve_simt_kernel<T, IA_COSINE>, (const T*)nullptr); break;    \
+      case IA_L1: rc = launch(retrieve_simt_kernel<T, IA_L1>, (const T*)nullptr); break;            \
+      default: rc = launch(retrieve_simt_kernel<T, IA_L2>, (const T*)nullptr); break;               \
+    }
+    if (cat->dtype == IA_F32) { IA_SIMT_DISPATCH(float) }
+    else if (cat->dtype == IA_BF16) { IA_SIMT_DISPATCH(__nv_bfloat16) }
+    else { IA_SIMT_DISPATCH(__half) }
+#undef IA_SIMT_DISPATCH
+    if (rc != IA_OK) return rc;
+  }
+  const int64_t mwant = (q + 7) / 8;
+  const int mgrid = (int)(mwant < 4 * sms ? mwant : 4 * sms);
+  merge_lists_kernel<<<mgrid, 256, 0, s>>>(cat->lists, p.n_splits, q, p.n_qt, BM, kListCap, k, keys_out);
+  IA_LAUNCH_CHECK();
+  return IA_OK;
+}
+
+int ia_topk_merge(const uint64_t* keys_in, int parts, int64_t q, int k, uint64_t* keys_out, ia_stream_t stream) {
+  if (keys_in == nullptr || keys_out == nullptr || parts < 1 || q < 0 || k < 1 || k > IA_MAX_K) { set_error("bad arguments"); return IA_ERR_INVALID; }
+  if (q == 0) return IA_OK;
+  const int64_t mwant = (q + 7) / 8;
+  const int mgrid = (int)(mwant < 4 * sm_count() ? mwant : 4 * sm_count());
+  merge_lists_kernel<<<mgrid, 256, 0, (cudaStream_t)stream>>>(keys_in, parts, q, 0, 0, k, k, keys_out);
+  IA_LAUNCH_CHECK();
+  return IA_OK;
+}
+
+int ia_unpack_keys(const uint64_t* keys, int64_t count, int descending, float* scores, int64_t* rows, ia_stream_t stream) {
+  if (keys == nullptr || count < 0) { set_error("bad arguments"); return IA_ERR_INVALID; }
+  if (count == 0) return IA_OK;
+  const int64_t want = (count + 255) / 256;
+  const int grid = (int)(want < 8 * sm_count() ? want : 8 * sm_count());
+  unpack_keys_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(keys, count, descending, scores, rows);
+  IA_LAUNCH_CHECK();
+  return IA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,227 @@
+// Building blocks of catalog retrieval: sm_100a PTX wrappers (mbarrier, TMA, tcgen05/TMEM) and the
+// per-query streaming top-k machinery shared by the tensor-core and the CUDA-core all-pairs kernels.
+#pragma once
+#include "common.cuh"
+
+namespace ia {
+
+// ------------------------------------------------------------------------------------ keys
+// key = (goodness(score) << 32) | (0xFFFFFFFF - global_row); larger key == better candidate, ties on the
+// score go to the lower row.  goodness = orderable(score) for similarities (larger is better) and its
+// complement for distances.  key 0 is the "empty" sentinel (orderable() of a finite float is never 0).
+__device__ __forceinline__ uint32_t orderable_u32(float f) {
+  const uint32_t u = __float_as_uint(f + 0.0f);  // -0.0 -> +0.0 so equal scores compare equal
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_orderable_u32(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
+}
+template <bool DESC> __device__ __forceinline__ uint32_t goodness(float s) {
+  const uint32_t o = orderable_u32(s);
+  return DESC ? o : ~o;
+}
+template <bool DESC> __device__ __forceinline__ float score_of_goodness(uint32_t g) {
+  return from_orderable_u32(DESC ? g : ~g);
+}
+template <bool DESC> __device__ __forceinline__ uint64_t make_key(float s, uint32_t row) {
+  return ((uint64_t)goodness<DESC>(s) << 32) | (uint64_t)(0xFFFFFFFFu - row);
+}
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kListCap = 128;   // IA_MAX_K: list entries per query (4 per lane)
+constexpr int kBufSlots = 16;   // append-buffer slots per query
+constexpr int kBufPitch = kBufSlots + 1;  // u64 words per query in shared memory (padded)
+
+// Warp-cooperative merge of up to 32 new keys (one per lane, 0 = none) into a sorted (descending) list of
+// <= 128 keys held 4 per lane: Lr[r] is position lane + 32*r.  Rank based: every existing entry moves down
+// by the number of new keys larger than it, every new key lands at (#list entries larger) + (#new keys
+// larger).  Writes the first k positions to `list` and returns the key at position k-1 (0 if the merged
+// list is shorter than k) to all lanes.
+__device__ __forceinline__ uint64_t warp_merge_keys(const uint64_t (&Lr)[4], uint64_t bk, int k, uint64_t* list) {
+  const int lane = threadIdx.x & 31;
+  int shift0 = 0, shift1 = 0, shift2 = 0, shift3 = 0, mypos = 0;
+  unsigned has = __ballot_sync(kFull, bk != 0);
+  while (has) {
+    const int t = __ffs(has) - 1;
+    has &= has - 1;
+    const uint64_t b = __shfl_sync(kFull, bk, t);
+    const bool g0 = Lr[0] > b, g1 = Lr[1] > b, g2 = Lr[2] > b, g3 = Lr[3] > b;
+    int cnt = __popc(__ballot_sync(kFull, g0)) + __popc(__ballot_sync(kFull, g1)) +
+              __popc(__ballot_sync(kFull, g2)) + __popc(__ballot_sync(kFull, g3)) +
+              __popc(__ballot_sync(kFull, bk > b));
+    shift0 += !g0; shift1 += !g1; shift2 += !g2; shift3 += !g3;
+    if (lane == t) mypos = cnt;
+  }
+  __syncwarp();
+  uint64_t kth = 0;
+  const int sh[4] = {shift0, shift1, shift2, shift3};
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    if (Lr[r] != 0) {
+      const int p = lane + 32 * r + sh[r];
+      if (p < k) {
+        list[p] = Lr[r];
+        if (p == k - 1) kth = Lr[r];
+      }
+    }
+  }
+  if (bk != 0 && mypos < k) {
+    list[mypos] = bk;
+    if (mypos == k - 1) kth = bk;
+  }
+  __syncwarp();
+  const uint32_t lo = __reduce_or_sync(kFull, (uint32_t)kth);
+  const uint32_t hi = __reduce_or_sync(kFull, (uint32_t)(kth >> 32));
+  return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ void warp_load_list(uint64_t (&Lr)[4], const uint64_t* list) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) Lr[r] = list[lane + 32 * r];
+}
+
+// Streaming top-k state of ONE query, owned by one thread; 32 queries (one warp) are compacted together.
+//   thr_key : candidates must beat this key (max of the local k-th best key and the k-th best goodness any
+//             other CTA has published for this query, tau_global)
+//   cnt     : filled slots of this query's append buffer (shared memory, kBufPitch u64 per query)
+struct TopKThread {
+  uint64_t thr_key;
+  int cnt;
+};
+
+// Compact the append buffers of every lane whose buffer holds >= min_cnt keys into its global list.
+// buf_warp: this warp's 32 append buffers; lists_warp: this warp's 32 lists (kListCap u64 each).
+// Must be called by all 32 lanes.  tau_global may be null.
+__device__ __forceinline__ void warp_compact(TopKThread& st, int min_cnt, int k, uint64_t* buf_warp,
+                                             uint64_t* lists_warp, uint32_t* tau_global_warp) {
+  const int lane = threadIdx.x & 31;
+  unsigned need = __ballot_sync(kFull, st.cnt >= min_cnt && st.cnt > 0);
+  while (need) {
+    const int ql = __ffs(need) - 1;
+    need &= need - 1;
+    const int c = __shfl_sync(kFull, st.cnt, ql);
+    uint64_t* list = lists_warp + (size_t)ql * kListCap;
+    uint64_t Lr[4];
+    warp_load_list(Lr, list);
+    const uint64_t bk = lane < c ? buf_warp[ql * kBufPitch + lane] : 0ull;
+    const uint64_t kth = warp_merge_keys(Lr, bk, k, list);
+    if (lane == ql) {
+      st.cnt = 0;
+      if (kth > st.thr_key) st.thr_key = kth;
+      if (tau_global_warp != nullptr && kth != 0) atomicMax(tau_global_warp + ql, (uint32_t)(kth >> 32));
+    }
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trap (an error the host sees), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > 200000000u) {
+      printf("ia_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+// TMA: 2-D tiled bulk tensor load global -> shared, completion on an mbarrier (SASS: UTMALDG)
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+// TMEM allocation (one warp), 512 columns = the whole tensor memory of the SM
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] . B[smem]^T, bf16/fp16 inputs, fp32 accumulate (SASS: UTCHMMA)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued MMAs of this thread arrive on the mbarrier when they complete
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns of TMEM -> 32 registers per thread (SASS: LDTM)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld_1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor for a K-major operand tile staged by TMA with 128-byte swizzle:
+// rows of 64 bf16 (128 B), 8-row groups 1024 B apart (SBO), version 1 (Blackwell), layout SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);        // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                              // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024u >> 4) << 32;                   // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                              // descriptor version, bits [46,48)
+  d |= (uint64_t)2 << 61;                              // layout type SWIZZLE_128B, bits [61,64)
+  return d;
+}
+// Instruction descriptor: fp32 accumulate, A and B K-major, dense; ab_format 0 = fp16, 1 = bf16.
+__host__ __device__ constexpr uint32_t umma_idesc(int m, int n, int ab_format) {
+  return (1u << 4) | ((uint32_t)ab_format << 7) | ((uint32_t)ab_format << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+
+}  // namespace ia

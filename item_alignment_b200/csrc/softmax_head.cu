@@ -1,0 +1,280 @@
+// "softmax" similarity measure: TwoTowerClassificationHead (reference src/models/base.py:103-117)
+// fused with CrossEntropyLoss forward + backward (reference src/models/text.py:1408-1409,1473).
+//
+//   logits = [x ; y] . W^T + b     W: [2, 2h] fp32        probs = softmax(logits)
+//
+// HBM-bound like the pair kernels: one warp owns one pair, x and y rows are read once into registers
+// (the torch.cat copy of the reference never exists), W lives in shared memory, and dx, dy are written
+// from the same registers.  dW is accumulated in registers per lane over all rows a warp visits and
+// reduced block -> workspace -> finalize kernel in a fixed order (bit-reproducible run to run).
+// Two classes: delta = p1 - label is formed without cancellation (label 1 -> -p0), dlogit1 = delta,
+// dlogit0 = -delta, so dW[0] = -dW[1] and db[0] = -db[1].
+#include "common.cuh"
+
+namespace ia {
+
+struct HeadParams {
+  const void* x;
+  const void* y;
+  int64_t ldx, ldy;
+  const float* w;   // [2, 2h]
+  const float* b;   // [2]
+  const int64_t* labels;
+  int64_t n;
+  int h;
+  float* logits;    // [n,2] or null
+  float* probs;     // [n,2] or null
+  float* loss_out;  // scalar
+  void* dx;
+  void* dy;
+  int64_t lddx, lddy;
+  float grad_scale;   // upstream / n
+  double loss_scale;  // 1/n
+  void* workspace;    // [kWorkspaceBytes | float partial[grid][2h+2]]
+};
+
+constexpr int kHeadMaxGrid = 592;  // 148 SMs x 4
+
+template <typename T, typename G, bool TRAIN, int VPL>
+__global__ void __launch_bounds__(256) softmax_head_kernel(const HeadParams p) {
+  constexpr int E = VecTraits<T>::kElems;
+  extern __shared__ float smem[];
+  float* sw = smem;                 // [2][2h]
+  float* sacc = smem + 4 * p.h;     // [2h] block accumulator of dW[1] (TRAIN)
+  const int h = p.h, h2 = 2 * p.h;
+  for (int i = threadIdx.x; i < 2 * h2; i += blockDim.x) sw[i] = p.w[i];
+  if (TRAIN)
+    for (int i = threadIdx.x; i < h2; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const float b0 = p.b[0], b1 = p.b[1];
+
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warps_total = (int64_t)gridDim.x * 8;
+  const int nvec = h / E;
+  float accx[TRAIN ? VPL * E : 1], accy[TRAIN ? VPL * E : 1];
+  if (TRAIN) {
+#pragma unroll
+    for (int i = 0; i < VPL * E; ++i) { accx[i] = 0.f; accy[i] = 0.f; }
+  }
+  float loss_acc = 0.f, db_acc = 0.f;
+
+  for (int64_t row = (int64_t)blockIdx.x * 8 + wib; row < p.n; row += warps_total) {
+    const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + row * p.ldx);
+    const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + row * p.ldy);
+    uint4 xv[VPL], yv[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) { xv[i] = ldg_stream(xr + v); yv[i] = ldg_stream(yr + v); }
+      else { xv[i] = make_uint4(0, 0, 0, 0); yv[i] = make_uint4(0, 0, 0, 0); }
+    }
+    int label = 0;
+    if (TRAIN) label = (int)(__ldg(p.labels + row) != 0);
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        float fx[E], fy[E];
+        unpack<T>(xv[i], fx);
+        unpack<T>(yv[i], fy);
+        const int c = v * E;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+          l0 = fmaf(fx[j], sw[c + j], l0);
+          l0 = fmaf(fy[j], sw[h + c + j], l0);
+          l1 = fmaf(fx[j], sw[h2 + c + j], l1);
+          l1 = fmaf(fy[j], sw[h2 + h + c + j], l1);
+        }
+      }
+    }
+    l0 = warp_sum(l0) + b0;
+    l1 = warp_sum(l1) + b1;
+    const float m = fmaxf(l0, l1);
+    const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+    const float den = e0 + e1;
+    const float p0 = e0 / den, p1 = e1 / den;
+    if (lane == 0) {
+      if (p.logits) { p.logits[2 * row] = l0; p.logits[2 * row + 1] = l1; }
+      if (p.probs) { p.probs[2 * row] = p0; p.probs[2 * row + 1] = p1; }
+    }
+    if (!TRAIN) continue;
+    loss_acc += logf(den) - ((label ? l1 : l0) - m);   // -log softmax[label]
+    const float delta = (label ? -p0 : p1) * p.grad_scale;   // d loss / d logit1 ( = -d loss / d logit0 )
+    db_acc += delta;
+    G* dxr = p.dx ? static_cast<G*>(p.dx) + row * p.lddx : nullptr;
+    G* dyr = p.dy ? static_cast<G*>(p.dy) + row * p.lddy : nullptr;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        float fx[E], fy[E], gx[E], gy[E];
+        unpack<T>(xv[i], fx);
+        unpack<T>(yv[i], fy);
+        const int c = v * E;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+          accx[i * E + j] = fmaf(delta, fx[j], accx[i * E + j]);
+          accy[i * E + j] = fmaf(delta, fy[j], accy[i * E + j]);
+          gx[j] = delta * (sw[h2 + c + j] - sw[c + j]);
+          gy[j] = delta * (sw[h2 + h + c + j] - sw[h + c + j]);
+        }
+        if (dxr) {
+          Packer<G, E>::store(dxr + (int64_t)v * E, gx);
+          Packer<G, E>::store(dyr + (int64_t)v * E, gy);
+        }
+      }
+    }
+  }
+
+  if (TRAIN) {
+    // fixed-order block reduction of the per-lane dW accumulators: warp 0, then warp 1, ...
+    for (int w = 0; w < 8; ++w) {
+      if (wib == w) {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const int v = lane + 32 * i;
+          if (v < nvec) {
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+              sacc[v * E + j] += accx[i * E + j];
+              sacc[h + v * E + j] += accy[i * E + j];
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    __shared__ float wl[8], wdb[8];
+    if (lane == 0) { wl[wib] = loss_acc; wdb[wib] = db_acc; }
+    __syncthreads();
+    float* part = reinterpret_cast<float*>(static_cast<char*>(p.workspace) + kWorkspaceBytes) +
+                  (size_t)blockIdx.x * (h2 + 2);
+    for (int i = threadIdx.x; i < h2; i += blockDim.x) part[i] = sacc[i];
+    double blk = 0.0;
+    if (threadIdx.x == 0) {
+      float dbs = 0.f;
+      for (int w = 0; w < 8; ++w) { blk += (double)wl[w]; dbs += wdb[w]; }
+      part[h2] = dbs;
+    }
+    grid_sum_finish(blk, p.workspace, p.loss_out, p.loss_scale);
+  }
+}
+
+// dW[1][j] = sum over blocks (index order) of partial[b][j]; dW[0] = -dW[1]; same for db.
+__global__ void __launch_bounds__(256) softmax_head_finalize(const float* partials, int nblocks, int h2, float* dw,
+                                                             float* db) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > h2) return;
+  float acc = 0.f;
+  for (int b = 0; b < nblocks; ++b) acc += partials[(size_t)b * (h2 + 2) + j];
+  if (j < h2) {
+    if (dw) { dw[h2 + j] = acc; dw[j] = -acc; }
+  } else if (db) {
+    db[1] = acc; db[0] = -acc;
+  }
+}
+
+template <typename T, typename G, bool TRAIN, int VPL>
+static int launch_head_one(const HeadParams& p, cudaStream_t stream, float* dw, float* db) {
+  auto kernel = softmax_head_kernel<T, G, TRAIN, VPL>;
+  const size_t smem = sizeof(float) * (TRAIN ? 6 : 4) * p.h;
+  static bool configured = false;
+  static int bps = 0;
+  static size_t configured_smem = 0;
+  if (!configured || smem > configured_smem) {
+    IA_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bps = blocks_per_sm(kernel, 256, smem);
+    configured = true;
+    configured_smem = smem;
+  }
+  int64_t want = (p.n + 7) / 8;
+  int64_t cap = (int64_t)sm_count() * bps;
+  if (cap > kHeadMaxGrid) cap = kHeadMaxGrid;
+  const int grid = (int)(want < cap ? want : cap);
+  kernel<<<grid, 256, smem, stream>>>(p);
+  IA_LAUNCH_CHECK();
+  if (TRAIN && (dw || db)) {
+    const float* partials = reinterpret_cast<const float*>(static_cast<const char*>(p.workspace) + kWorkspaceBytes);
+    const int h2 = 2 * p.h;
+    softmax_head_finalize<<<(h2 + 1 + 255) / 256, 256, 0, stream>>>(partials, grid, h2, dw, db);
+    IA_LAUNCH_CHECK();
+  }
+  return IA_OK;
+}
+
+template <typename T, typename G>
+static int launch_head(const HeadParams& p, bool train, cudaStream_t stream, float* dw, float* db) {
+  const int nvec = p.h / VecTraits<T>::kElems;
+  if (train) {
+    if (nvec <= 64) return launch_head_one<T, G, true, 2>(p, stream, dw, db);
+    if (nvec <= 128) return launch_head_one<T, G, true, 4>(p, stream, dw, db);
+    return launch_head_one<T, G, true, 8>(p, stream, dw, db);
+  }
+  if (nvec <= 64) return launch_head_one<T, G, false, 2>(p, stream, dw, db);
+  if (nvec <= 128) return launch_head_one<T, G, false, 4>(p, stream, dw, db);
+  return launch_head_one<T, G, false, 8>(p, stream, dw, db);
+}
+
+}  // namespace ia
+
+using namespace ia;
+
+extern "C" {
+
+size_t ia_softmax_head_workspace_bytes(int64_t h) {
+  return kWorkspaceBytes + sizeof(float) * (size_t)kHeadMaxGrid * (size_t)(2 * h + 2);
+}
+
+int ia_softmax_head_fwd_bwd(int dtype, int grad_dtype, const void* x, const void* y, int64_t ldx, int64_t ldy,
+                            const float* w, const float* b, const int64_t* labels, int64_t n, int64_t h,
+                            float* logits, float* probs, float* loss_out, void* dx, void* dy, int64_t lddx,
+                            int64_t lddy, float* dw, float* db, float grad_scale, void* workspace,
+                            size_t workspace_bytes, ia_stream_t stream) {
+  if (n < 0 || h <= 0 || ldx < h || ldy < h || w == nullptr || b == nullptr || (n > 0 && (x == nullptr || y == nullptr))) {
+    set_error("bad arguments");
+    return IA_ERR_INVALID;
+  }
+  const bool train = labels != nullptr;
+  if (train && loss_out == nullptr) { set_error("loss_out must not be NULL when labels are given"); return IA_ERR_INVALID; }
+  if ((dx == nullptr) != (dy == nullptr)) { set_error("dx and dy must both be given or both be NULL"); return IA_ERR_INVALID; }
+  if (grad_dtype != dtype && grad_dtype != IA_F32) { set_error("grad_dtype must equal dtype or be fp32"); return IA_ERR_UNSUPPORTED; }
+  if (train && (workspace == nullptr || workspace_bytes < ia_softmax_head_workspace_bytes(h))) {
+    set_error("workspace too small: need %zu bytes", ia_softmax_head_workspace_bytes(h));
+    return IA_ERR_WORKSPACE;
+  }
+  const int elems = dtype == IA_F32 ? 4 : 8;
+  const size_t es = dtype == IA_F32 ? 4 : 2, gs = grad_dtype == IA_F32 ? 4 : 2;
+  auto al = [](const void* ptr, int64_t ld, size_t e) { return reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && (ld * (int64_t)e) % 16 == 0; };
+  if (h % elems != 0 || h / elems > 256 || !al(x, ldx, es) || !al(y, ldy, es) ||
+      (dx && (!al(dx, lddx, gs) || !al(dy, lddy, gs) || lddx < h || lddy < h))) {
+    set_error("softmax head kernel needs 16-byte aligned rows, h %% %d == 0 and h <= %d", elems, 256 * elems);
+    return IA_ERR_UNSUPPORTED;
+  }
+  if (6 * h * sizeof(float) > 200 * 1024) { set_error("h too large for the shared-memory W tile"); return IA_ERR_UNSUPPORTED; }
+  if (n == 0) {
+    if (train) {
+      const float v = __builtin_nanf("");
+      IA_CUDA_CHECK(cudaMemcpyAsync(loss_out, &v, sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+      if (dw) IA_CUDA_CHECK(cudaMemsetAsync(dw, 0, sizeof(float) * 4 * h, (cudaStream_t)stream));
+      if (db) IA_CUDA_CHECK(cudaMemsetAsync(db, 0, sizeof(float) * 2, (cudaStream_t)stream));
+    }
+    return IA_OK;
+  }
+  HeadParams p{};
+  p.x = x; p.y = y; p.ldx = ldx; p.ldy = ldy; p.w = w; p.b = b; p.labels = labels; p.n = n; p.h = (int)h;
+  p.logits = logits; p.probs = probs; p.loss_out = loss_out; p.dx = dx; p.dy = dy; p.lddx = lddx; p.lddy = lddy;
+  p.grad_scale = (float)((double)grad_scale / (double)n);
+  p.loss_scale = 1.0 / (double)n;
+  p.workspace = workspace;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == IA_F32) return launch_head<float, float>(p, train, s, dw, db);
+  if (dtype == IA_BF16 && grad_dtype == IA_BF16) return launch_head<__nv_bfloat16, __nv_bfloat16>(p, train, s, dw, db);
+  if (dtype == IA_BF16) return launch_head<__nv_bfloat16, float>(p, train, s, dw, db);
+  if (dtype == IA_F16 && grad_dtype == IA_F16) return launch_head<__half, __half>(p, train, s, dw, db);
+  if (dtype == IA_F16) return launch_head<__half, float>(p, train, s, dw, db);
+  set_error("unsupported dtype %d", dtype);
+  return IA_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

@@ -1,0 +1,343 @@
+"""Functional API over the C ABI: torch tensors in, torch tensors out, autograd wired.
+
+torch is plumbing here (device memory, streams, autograd graph); every score / loss / gradient value is
+produced by the CUDA kernels of libia_b200.so.  Non-CUDA tensors raise: there is no CPU path.
+"""
+import torch
+
+from . import _lib
+from ._lib import LOSSES, MEASURES, REDUCTIONS, check, lib
+
+_DT = {torch.float32: _lib.IA_F32, torch.bfloat16: _lib.IA_BF16, torch.float16: _lib.IA_F16}
+_workspaces = {}
+
+
+def _measure_id(measure):
+    if measure not in MEASURES:
+        raise ValueError(f"Unsupported similarty measure: {measure}")     # wording of reference base.py:64
+    return MEASURES[measure]
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _prep(x, y):
+    if not (x.is_cuda and y.is_cuda):
+        raise RuntimeError("item_alignment_b200 runs on CUDA tensors only (no CPU fallback)")
+    if x.dim() != 2 or x.shape != y.shape:
+        raise ValueError(f"expected two [N, D] tensors of equal shape, got {tuple(x.shape)} and {tuple(y.shape)}")
+    if x.dtype != y.dtype:
+        y = y.to(x.dtype)
+    if x.dtype not in _DT:
+        raise NotImplementedError(f"unsupported dtype {x.dtype}")
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    if y.stride(1) != 1:
+        y = y.contiguous()
+    return x, y
+
+
+def workspace(device, nbytes=None):
+    """Zero-initialised scratch for the deterministic loss reduction, one per (device, stream)."""
+    need = nbytes or lib().ia_workspace_bytes()
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(need, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _ld(t):
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+
+# ------------------------------------------------------------------------------------------- raw ops
+def pair_score_raw(measure, x, y, threshold=None, want_probs=True):
+    """sim [, probs [, labels]] with no autograd (reference base.py:77-86, finetune_text.py:576-580)."""
+    x, y = _prep(x, y)
+    n, d = x.shape
+    sim = torch.empty(n, dtype=torch.float32, device=x.device)
+    probs = torch.empty(n, dtype=torch.float32, device=x.device) if (want_probs or threshold is not None) else None
+    labels = torch.empty(n, dtype=torch.bool, device=x.device) if threshold is not None else None
+    with torch.cuda.device(x.device):
+        check(lib().ia_pair_score_fwd(_measure_id(measure), _DT[x.dtype], x.data_ptr(), y.data_ptr(), n, d, _ld(x), _ld(y),
+                                      sim.data_ptr(), probs.data_ptr() if probs is not None else None,
+                                      float(threshold) if threshold is not None else 0.0,
+                                      labels.data_ptr() if labels is not None else None, _stream()))
+    return sim, probs, labels
+
+
+def pair_score_bwd_raw(measure, x, y, gsim, grad_dtype=None):
+    x, y = _prep(x, y)
+    n, d = x.shape
+    gd = grad_dtype or x.dtype
+    dx = torch.empty((n, d), dtype=gd, device=x.device)
+    dy = torch.empty((n, d), dtype=gd, device=x.device)
+    gsim = gsim.detach().to(torch.float32).contiguous()
+    with torch.cuda.device(x.device):
+        check(lib().ia_pair_score_bwd(_measure_id(measure), _DT[x.dtype], _DT[gd], x.data_ptr(), y.data_ptr(), _ld(x), _ld(y),
+                                      gsim.data_ptr(), n, d, dx.data_ptr(), dy.data_ptr(), d, d, _stream()))
+    return dx, dy
+
+
+def pair_score_loss_raw(measure, loss_type, x, y, labels, margin=1.0, reduction="mean", grad_dtype=None,
+                        grad_scale=1.0, want_grads=True):
+    """ONE kernel: sim, probs, loss, dx, dy (reference head + ladder + backward; see include/ia_b200.h)."""
+    x, y = _prep(x, y)
+    n, d = x.shape
+    if loss_type not in LOSSES:
+        raise ValueError(f"unsupported loss_type for a vector-similarity head: {loss_type}")
+    labels = labels.view(-1)
+    if labels.dtype != torch.int64:
+        labels = labels.to(torch.int64)      # bce: float labels are accepted, {0,1} semantics
+    labels = labels.contiguous()
+    if labels.numel() != n:
+        raise ValueError("labels must have one entry per pair")
+    gd = grad_dtype or x.dtype
+    dev = x.device
+    sim = torch.empty(n, dtype=torch.float32, device=dev)
+    probs = torch.empty(n, dtype=torch.float32, device=dev)
+    loss = torch.empty(n if reduction == "none" else 1, dtype=torch.float32, device=dev)
+    dx = torch.empty((n, d), dtype=gd, device=dev) if want_grads else None
+    dy = torch.empty((n, d), dtype=gd, device=dev) if want_grads else None
+    with torch.cuda.device(dev):
+        ws = workspace(dev)
+        check(lib().ia_pair_score_loss_fwd_bwd(
+            _measure_id(measure), LOSSES[loss_type], float(margin), REDUCTIONS[reduction], _DT[x.dtype], _DT[gd],
+            x.data_ptr(), y.data_ptr(), _ld(x), _ld(y), labels.data_ptr(), n, d, sim.data_ptr(), probs.data_ptr(),
+            loss.data_ptr(), dx.data_ptr() if want_grads else None, dy.data_ptr() if want_grads else None, d, d,
+            float(grad_scale), ws.data_ptr(), ws.numel(), _stream()))
+    return sim, probs, (loss if reduction == "none" else loss[0]), dx, dy
+
+
+def scale_inplace_(a, b, g):
+    """a *= g, b *= g with g a device scalar; the kernel is a no-op when g == 1 (no host sync)."""
+    g = g.detach().to(torch.float32).reshape(1)
+    with torch.cuda.device(a.device):
+        check(lib().ia_scale_inplace(_DT[a.dtype], a.data_ptr(), b.data_ptr() if b is not None else None, a.numel(),
+                                     g.data_ptr(), _stream()))
+
+
+def score_loss_raw(loss_type, sim, target, margin=1.0, reduction="mean", want_grad=True):
+    """HingeLoss / EuclideanDistanceLoss / BCEWithLogits on a score vector (reference loss.py)."""
+    sim = sim.detach().to(torch.float32).contiguous().view(-1)
+    target = target.view(-1).to(torch.int64).contiguous()
+    n = sim.numel()
+    out = torch.empty(n if reduction == "none" else 1, dtype=torch.float32, device=sim.device)
+    g = torch.empty(n, dtype=torch.float32, device=sim.device) if want_grad else None
+    with torch.cuda.device(sim.device):
+        ws = workspace(sim.device)
+        check(lib().ia_score_loss_fwd_bwd(LOSSES[loss_type], float(margin), REDUCTIONS[reduction], sim.data_ptr(),
+                                          target.data_ptr(), n, out.data_ptr(), g.data_ptr() if want_grad else None, 1.0,
+                                          ws.data_ptr(), ws.numel(), _stream()))
+    return (out if reduction == "none" else out[0]), g
+
+
+def softmax_head_raw(x, y, w, b, labels=None, grad_dtype=None, want_grads=True, grad_scale=1.0):
+    """TwoTowerClassificationHead (+ CrossEntropyLoss fwd/bwd when labels are given), reference base.py:103-117."""
+    x, y = _prep(x, y)
+    n, h = x.shape
+    dev = x.device
+    w = w.detach().to(torch.float32).contiguous()
+    b = b.detach().to(torch.float32).contiguous()
+    if w.shape != (2, 2 * h) or b.shape != (2,):
+        raise NotImplementedError("the CUDA softmax head supports num_labels == 2")
+    logits = torch.empty((n, 2), dtype=torch.float32, device=dev)
+    probs = torch.empty((n, 2), dtype=torch.float32, device=dev)
+    train = labels is not None
+    gd = grad_dtype or x.dtype
+    loss = dx = dy = dw = db = None
+    ws_ptr, ws_n = None, 0
+    with torch.cuda.device(dev):
+        if train:
+            labels = labels.view(-1).to(torch.int64).contiguous()
+            loss = torch.empty(1, dtype=torch.float32, device=dev)
+            if want_grads:
+                dx = torch.empty((n, h), dtype=gd, device=dev)
+                dy = torch.empty((n, h), dtype=gd, device=dev)
+                dw = torch.empty((2, 2 * h), dtype=torch.float32, device=dev)
+                db = torch.empty(2, dtype=torch.float32, device=dev)
+            ws = workspace(dev, lib().ia_softmax_head_workspace_bytes(h))
+            ws_ptr, ws_n = ws.data_ptr(), ws.numel()
+        check(lib().ia_softmax_head_fwd_bwd(
+            _DT[x.dtype], _DT[gd], x.data_ptr(), y.data_ptr(), _ld(x), _ld(y), w.data_ptr(), b.data_ptr(),
+            labels.data_ptr() if train else None, n, h, logits.data_ptr(), probs.data_ptr(),
+            loss.data_ptr() if train else None, dx.data_ptr() if dx is not None else None,
+            dy.data_ptr() if dy is not None else None, h, h, dw.data_ptr() if dw is not None else None,
+            db.data_ptr() if db is not None else None, float(grad_scale), ws_ptr, ws_n, _stream()))
+    return logits, probs, (loss[0] if train else None), dx, dy, dw, db
+
+
+def row_inv_norm(x, eps=1e-8):
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().ia_row_inv_norm(_DT[x.dtype], x.data_ptr(), x.shape[0], x.shape[1], _ld(x), float(eps), out.data_ptr(), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------- autograd
+class _PairScoreFn(torch.autograd.Function):
+    """sim = similarity(x, y) with the backward kernel (unfused head -> loss module sequence of the reference)."""
+
+    @staticmethod
+    def forward(ctx, x, y, measure):
+        sim, _, _ = pair_score_raw(measure, x, y, want_probs=False)
+        ctx.save_for_backward(x, y)
+        ctx.measure = measure
+        return sim
+
+    @staticmethod
+    def backward(ctx, gsim):
+        x, y = ctx.saved_tensors
+        dx, dy = pair_score_bwd_raw(ctx.measure, x, y, gsim)
+        return dx.to(x.dtype), dy.to(y.dtype), None
+
+
+class _FusedPairLossFn(torch.autograd.Function):
+    """(loss, sim, probs) from ONE kernel that also produced dx, dy; backward only rescales by the upstream
+    scalar (a device-side no-op when it is 1)."""
+
+    @staticmethod
+    def forward(ctx, x, y, labels, measure, loss_type, margin, reduction):
+        need = x.requires_grad or y.requires_grad
+        sim, probs, loss, dx, dy = pair_score_loss_raw(measure, loss_type, x, y, labels, margin, reduction, want_grads=need)
+        ctx.need = need
+        if need:
+            ctx.save_for_backward(dx, dy)
+        ctx.mark_non_differentiable(sim, probs)
+        return loss, sim, probs
+
+    @staticmethod
+    def backward(ctx, gloss, _gsim, _gprobs):
+        dx, dy = ctx.saved_tensors
+        scale_inplace_(dx, dy, gloss)
+        return dx, dy, None, None, None, None, None
+
+
+class _ScoreLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sim, target, loss_type, margin, reduction):
+        out, g = score_loss_raw(loss_type, sim, target, margin, reduction, want_grad=sim.requires_grad)
+        if g is not None:
+            ctx.save_for_backward(g)
+        ctx.reduction = reduction
+        ctx.n = sim.numel()
+        ctx.in_dtype = sim.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (g,) = ctx.saved_tensors
+        return (g * gout).to(ctx.in_dtype), None, None, None, None
+
+
+class _SoftmaxHeadLogitsFn(torch.autograd.Function):
+    """logits of the two-tower softmax head; arbitrary upstream d/dlogits handled with library GEMMs
+    (this is the unfused drop-in path; the fused CE path is softmax_head_ce)."""
+
+    @staticmethod
+    def forward(ctx, x, y, w, b):
+        logits, _, _, _, _, _, _ = softmax_head_raw(x, y, w, b)
+        ctx.save_for_backward(x, y, w)
+        return logits
+
+    @staticmethod
+    def backward(ctx, gl):
+        x, y, w = ctx.saved_tensors
+        h = x.shape[1]
+        gl = gl.float()
+        wf = w.float()
+        dx = (gl @ wf[:, :h]).to(x.dtype)
+        dy = (gl @ wf[:, h:]).to(y.dtype)
+        dw = torch.cat((gl.t() @ x.float(), gl.t() @ y.float()), dim=1).to(w.dtype)
+        return dx, dy, dw, gl.sum(0)
+
+
+class _FusedSoftmaxCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, w, b, labels):
+        logits, probs, loss, dx, dy, dw, db = softmax_head_raw(x, y, w, b, labels)
+        ctx.save_for_backward(dx, dy, dw, db)
+        ctx.wdtype, ctx.bdtype = w.dtype, b.dtype
+        ctx.mark_non_differentiable(logits, probs)
+        return loss, logits, probs
+
+    @staticmethod
+    def backward(ctx, gloss, _gl, _gp):
+        dx, dy, dw, db = ctx.saved_tensors
+        scale_inplace_(dx, dy, gloss)
+        scale_inplace_(dw, None, gloss)
+        scale_inplace_(db, None, gloss)
+        return dx, dy, dw.to(ctx.wdtype), db.to(ctx.bdtype), None
+
+
+# ------------------------------------------------------------------------------------------- public
+def pair_similarity(measure, x, y):
+    """similarity(x, y) -> [N] fp32, differentiable (reference base.py:54-62,77)."""
+    if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad):
+        x, y = _prep(x, y)
+        return _PairScoreFn.apply(x, y, measure)
+    return pair_score_raw(measure, x, y, want_probs=False)[0]
+
+
+def probs_of(measure, sim):
+    """reference base.py:79-86 on an autograd-tracked sim (tiny [N] torch ops)."""
+    if measure == "cosine":
+        return (sim + 1) / 2
+    if measure in ("l1", "l2"):
+        return torch.exp(-sim)
+    if measure == "inner_product":
+        return torch.sigmoid(sim)
+    raise ValueError(f"Unsupported similarty measure: {measure}")
+
+
+def pair_score(measure, x, y, threshold=None):
+    """(sim, probs[, labels]): one kernel when no gradient is needed."""
+    if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad):
+        sim = pair_similarity(measure, x, y)
+        probs = probs_of(measure, sim)
+        if threshold is None:
+            return sim, probs
+        return sim, probs, probs.detach().double() >= float(threshold)
+    sim, probs, labels = pair_score_raw(measure, x, y, threshold)
+    return (sim, probs) if threshold is None else (sim, probs, labels)
+
+
+def pair_score_loss(measure, loss_type, x, y, labels, margin=1.0, reduction="mean"):
+    """Fused head score + loss ladder + backward: returns (sim, probs, loss); loss.backward() hands the
+    gradients computed in the same pass to autograd."""
+    if reduction == "none":
+        sim = pair_similarity(measure, x, y)
+        probs = probs_of(measure, sim)
+        if loss_type == "cosine":
+            raise NotImplementedError("reduction='none' is not offered for the cosine-embedding loss")
+        target = labels if loss_type == "bce" else labels * 2 - 1
+        return sim, probs, _ScoreLossFn.apply(sim, target, loss_type, margin, "none")
+    x, y = _prep(x, y)
+    loss, sim, probs = _FusedPairLossFn.apply(x, y, labels, measure, loss_type, float(margin), reduction)
+    return sim, probs, loss
+
+
+def score_loss(loss_type, sim, target, margin=1.0, reduction="mean"):
+    return _ScoreLossFn.apply(sim, target, loss_type, float(margin), reduction)
+
+
+def softmax_head(x, y, w, b):
+    """(logits, probs) of the two-tower softmax head, differentiable."""
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (x, y, w, b)):
+        x, y = _prep(x, y)
+        logits = _SoftmaxHeadLogitsFn.apply(x, y, w, b)
+        return logits, torch.softmax(logits, dim=1)
+    logits, probs, _, _, _, _, _ = softmax_head_raw(x, y, w, b)
+    return logits, probs
+
+
+def softmax_head_ce(x, y, w, b, labels):
+    """Fused softmax head + CrossEntropyLoss forward/backward: (logits, probs, loss)."""
+    x, y = _prep(x, y)
+    loss, logits, probs = _FusedSoftmaxCEFn.apply(x, y, w, b, labels)
+    return logits, probs, loss

@@ -1,0 +1,155 @@
+"""Catalog-scale same-item retrieval: all-pairs scores + per-query top-k, single GPU and row-sharded.
+
+No reference implementation exists (the README only motivates it, README.md:12,16); semantics are the
+reference's pairwise similarity (src/models/base.py:54-62) for every (query, catalog row), top-k by a stable
+sort -- ties go to the lower catalog row (nearest precedent: torchkge/torchkge/inference.py:243-246).
+
+Results travel as packed 64-bit keys (score goodness << 32 | ~row) so that one unsigned compare orders
+candidates identically inside the kernel epilogue, in the shard merge and after the NCCL all-gather.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import MEASURES, check, lib
+from .functional import _DT, _ld, _stream
+
+
+def shard_bounds(total_rows, world_size, rank):
+    """Contiguous row shard [lo, hi) of `rank` (shard r holds rows [r*ceil(C/G), ...))."""
+    per = -(-total_rows // world_size)
+    lo = min(rank * per, total_rows)
+    return lo, min(lo + per, total_rows)
+
+
+class CatalogIndex:
+    """Device-resident catalog [C, D] (borrowed) + inverse norms + TMA descriptor + scratch, behind an
+    opaque C handle.  `row_base` is the global id of local row 0 (shard offset)."""
+
+    def __init__(self, catalog, row_base=0):
+        if not catalog.is_cuda:
+            raise RuntimeError("item_alignment_b200 runs on CUDA tensors only (no CPU fallback)")
+        if catalog.dim() != 2 or catalog.dtype not in _DT:
+            raise ValueError("catalog must be a [C, D] fp32 / bf16 / fp16 CUDA tensor")
+        if catalog.stride(1) != 1:
+            catalog = catalog.contiguous()
+        self.catalog = catalog              # keep the borrowed memory alive
+        self.row_base = int(row_base)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(catalog.device):
+            check(lib().ia_catalog_create(ctypes.byref(self._h), _DT[catalog.dtype], catalog.data_ptr(), catalog.shape[0],
+                                          catalog.shape[1], _ld(catalog), self.row_base, _stream()))
+
+    def close(self):
+        if self._h:
+            torch.cuda.synchronize(self.catalog.device)
+            lib().ia_catalog_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def topk_keys(self, queries, k, measure="cosine"):
+        """[Q, k] uint64 keys (as int64 storage), best first."""
+        if measure not in MEASURES:
+            raise ValueError(f"Unsupported similarty measure: {measure}")
+        if not self._h:
+            raise RuntimeError("CatalogIndex is closed")
+        if not queries.is_cuda or queries.dim() != 2 or queries.shape[1] != self.catalog.shape[1]:
+            raise ValueError("queries must be a [Q, D] CUDA tensor with the catalog's D")
+        if queries.dtype != self.catalog.dtype:
+            queries = queries.to(self.catalog.dtype)
+        if queries.stride(1) != 1:
+            queries = queries.contiguous()
+        keys = torch.empty((queries.shape[0], k), dtype=torch.int64, device=queries.device)
+        with torch.cuda.device(queries.device):
+            check(lib().ia_catalog_topk(self._h, MEASURES[measure], queries.data_ptr(), queries.shape[0], _ld(queries), int(k),
+                                        keys.data_ptr(), _stream()))
+        return keys
+
+    def topk(self, queries, k, measure="cosine"):
+        """(scores [Q,k] fp32, rows [Q,k] int64 global ids), best first; -1 / +-inf where fewer than k rows exist."""
+        return unpack_keys(self.topk_keys(queries, k, measure), measure)
+
+
+def unpack_keys(keys, measure):
+    descending = measure in ("inner_product", "cosine")
+    scores = torch.empty(keys.shape, dtype=torch.float32, device=keys.device)
+    rows = torch.empty(keys.shape, dtype=torch.int64, device=keys.device)
+    with torch.cuda.device(keys.device):
+        check(lib().ia_unpack_keys(keys.data_ptr(), keys.numel(), int(descending), scores.data_ptr(), rows.data_ptr(), _stream()))
+    return scores, rows
+
+
+def merge_keys(parts, k):
+    """[G, Q, k] sorted key lists -> [Q, k] (the merge after the shard all-gather)."""
+    parts = parts.contiguous()
+    g, q, kk = parts.shape
+    if kk != k:
+        raise ValueError("merge_keys expects lists of length k")
+    out = torch.empty((q, k), dtype=torch.int64, device=parts.device)
+    with torch.cuda.device(parts.device):
+        check(lib().ia_topk_merge(parts.data_ptr(), g, q, k, out.data_ptr(), _stream()))
+    return out
+
+
+def all_gather_keys(keys, group=None):
+    """ONE collective per query batch: all-gather of the per-shard key lists [Q, k] -> [G, Q, k]
+    (NCCL over NVLink on the GPU box; gloo in the CPU tests of the host logic)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    keys = keys.contiguous()
+    # concatenated (not stacked) output layout: the form both NCCL and gloo accept
+    out = torch.empty((world * keys.shape[0],) + tuple(keys.shape[1:]), dtype=keys.dtype, device=keys.device)
+    dist.all_gather_into_tensor(out, keys, group=group)
+    return out.view((world,) + tuple(keys.shape))
+
+
+class ShardedCatalogIndex:
+    """Row-sharded retrieval over the ranks of a torch.distributed group (one process per GPU).
+
+    Each rank holds catalog rows [lo, hi) of the global catalog; queries are replicated; every rank computes its
+    local top-k as global-row keys, ONE all-gather ([Q,k] u64 per rank) moves them over NVLink, and every rank
+    merges the G lists with the same unsigned compare, so ties still break by global row."""
+
+    def __init__(self, local_catalog, total_rows, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.total_rows = int(total_rows)
+        lo, hi = shard_bounds(self.total_rows, self.world, self.rank)
+        if local_catalog.shape[0] != hi - lo:
+            raise ValueError(f"rank {self.rank} must hold rows [{lo}, {hi}) of the catalog, got {local_catalog.shape[0]} rows")
+        self.lo, self.hi = lo, hi
+        self.local = CatalogIndex(local_catalog, row_base=lo) if hi > lo else None
+
+    def close(self):
+        if self.local is not None:
+            self.local.close()
+
+    def gather_keys(self, keys):
+        return all_gather_keys(keys, self.group)
+
+    def topk_keys(self, queries, k, measure="cosine"):
+        if self.local is not None:
+            keys = self.local.topk_keys(queries, k, measure)
+        else:
+            keys = torch.zeros((queries.shape[0], k), dtype=torch.int64, device=queries.device)
+        if self.world == 1:
+            return keys
+        return merge_keys(self.gather_keys(keys), k)
+
+    def topk(self, queries, k, measure="cosine"):
+        return unpack_keys(self.topk_keys(queries, k, measure), measure)

@@ -84,3 +84,43 @@ def assert_grad_close(ours, ref, term_scale, scale, rtol, what="grad", skip_rows
     bad = fin & ~(err <= bound)
     assert not bad.any(), (f"{what}: {bad.sum()} of {bad.size} outside tolerance; worst "
                            f"{np.nanmax(np.where(fin, err / bound, 0)):.3g}x bound at row {np.argwhere(bad)[0][0]}")
+
+
+def assert_topk_matches(scores, idx, ref_matrix, k, descending, tol, exact=False):
+    """Top-k parity against a full oracle score matrix [Q, C].
+
+    exact=True: indices and scores bit-identical to the stable-sort top-k of ref_matrix.
+    Otherwise (GPU accumulation order != CPU order): per query
+      * scores match the oracle's sorted scores within tol,
+      * every returned row's oracle score is within tol of qualifying, every oracle row that beats the k-th
+        by more than tol is returned,
+      * wherever the oracle's neighbouring ranks are separated by more than 2*tol the index matches exactly.
+    Returns the number of (query, rank) positions that were gap-ambiguous."""
+    scores, idx = _np(scores), np.asarray(idx.detach().cpu().numpy() if hasattr(idx, "detach") else idx)
+    ref = np.asarray(ref_matrix, dtype=np.float64)
+    q, c = ref.shape
+    kk = min(k, c)
+    order = np.argsort(-ref if descending else ref, axis=1, kind="stable")[:, :kk]
+    top = np.take_along_axis(ref, order, 1)
+    if exact:
+        assert np.array_equal(idx[:, :kk], order), "top-k indices differ from the stable-sort oracle"
+        assert np.array_equal(scores[:, :kk].astype(np.float32), top.astype(np.float32)), "top-k scores differ"
+        return 0
+    assert np.all(np.abs(scores[:, :kk] - top) <= tol + 1e-6 * np.abs(top)), \
+        f"sorted scores differ by up to {np.abs(scores[:, :kk] - top).max():.3g} (tol {tol})"
+    sgn = -1.0 if descending else 1.0
+    ambiguous = 0
+    for i in range(q):
+        kth = top[i, kk - 1]
+        got = idx[i, :kk]
+        assert len(set(got.tolist())) == kk, f"query {i}: duplicate rows in the result"
+        got_ref = ref[i, got]
+        assert np.all(sgn * (got_ref - kth) <= tol + 1e-12), f"query {i}: a returned row does not qualify"
+        must = np.nonzero(sgn * (ref[i] - kth) < -tol)[0]
+        assert np.isin(must, got).all(), f"query {i}: a clearly better row is missing"
+        gaps_prev = np.abs(np.diff(top[i], prepend=top[i, 0] - sgn * 1e9))
+        gaps_next = np.abs(np.diff(top[i], append=(ref[i, np.argsort(sgn * ref[i], kind='stable')[kk]] if c > kk else top[i, -1] + sgn * 1e9)))
+        clear = (gaps_prev > 2 * tol) & (gaps_next > 2 * tol)
+        assert np.array_equal(got[clear], order[i][clear]), f"query {i}: index mismatch at a gap-separated rank"
+        ambiguous += int((~clear).sum())
+    return ambiguous
