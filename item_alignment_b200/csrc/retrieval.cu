@@ -173,38 +173,49 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           uint32_t r[32];
           tmem_ld_32x32(taddr + g * 32, r);
           tmem_ld_wait();
-          float m = -INFINITY;
+          // fast path: scale by 1/|c| and take the maximum of each 8-column block (2-3 instructions per score)
+          float v[32], m8[4];
           const float4* cs4 = reinterpret_cast<const float4*>(cs + g * 32);
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            float v0 = __uint_as_float(r[4 * c4 + 0]), v1 = __uint_as_float(r[4 * c4 + 1]);
-            float v2 = __uint_as_float(r[4 * c4 + 2]), v3 = __uint_as_float(r[4 * c4 + 3]);
-            if (COSINE) {
-              const float4 ci = cs4[c4];
-              v0 *= ci.x; v1 *= ci.y; v2 *= ci.z; v3 *= ci.w;
-            }
-            m = fmaxf(fmaxf(m, v0), fmaxf(v1, fmaxf(v2, v3)));
-          }
-          if (COSINE) m *= qinv;
-          if (__any_sync(kFull, q_ok && m >= thr_f)) {
-            // rare path: re-read this group's 32 columns one at a time and append the survivors
-#pragma unroll 1
-            for (int c = 0; c < 32; ++c) {
-              float s = __uint_as_float(tmem_ld_1(taddr + g * 32 + c));
-              tmem_ld_wait();
-              if (COSINE) s = (s * cs[g * 32 + c]) * qinv;
-              const int64_t j = j0 + g * 32 + c;
-              if (q_ok && j < p.c_rows && s >= thr_f) {
-                const uint64_t key = make_key<true>(s, p.row_base + (uint32_t)j);
-                if (key > st.thr_key) {
-                  buf_warp[lane * kBufPitch + st.cnt] = key;
-                  st.cnt++;
-                }
+          for (int b = 0; b < 4; ++b) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int c = 8 * b + 4 * h;
+              v[c + 0] = __uint_as_float(r[c + 0]); v[c + 1] = __uint_as_float(r[c + 1]);
+              v[c + 2] = __uint_as_float(r[c + 2]); v[c + 3] = __uint_as_float(r[c + 3]);
+              if (COSINE) {
+                const float4 ci = cs4[2 * b + h];
+                v[c + 0] *= ci.x; v[c + 1] *= ci.y; v[c + 2] *= ci.z; v[c + 3] *= ci.w;
               }
-              if (__any_sync(kFull, st.cnt == kBufSlots)) {
-                __syncwarp();
-                warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp);
-                thr_f = st.thr_key ? score_of_goodness<true>((uint32_t)(st.thr_key >> 32)) : -INFINITY;
+            }
+            m8[b] = fmaxf(fmaxf(fmaxf(v[8 * b], v[8 * b + 1]), fmaxf(v[8 * b + 2], v[8 * b + 3])),
+                          fmaxf(fmaxf(v[8 * b + 4], v[8 * b + 5]), fmaxf(v[8 * b + 6], v[8 * b + 7])));
+            if (COSINE) m8[b] *= qinv;     // x (1/|q|) > 0 is monotone: max commutes with it exactly
+          }
+          const float mg = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+          if (__any_sync(kFull, q_ok && mg >= thr_f)) {
+            // rare path, per 8-column block, straight from the registers
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              if (__any_sync(kFull, q_ok && m8[b] >= thr_f)) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const float s = COSINE ? v[8 * b + c] * qinv : v[8 * b + c];
+                  const int64_t j = j0 + g * 32 + 8 * b + c;
+                  if (q_ok && s >= thr_f && j < p.c_rows) {
+                    const uint64_t key = make_key<true>(s, p.row_base + (uint32_t)j);
+                    if (key > st.thr_key) {
+                      buf_warp[lane * kBufPitch + st.cnt] = key;
+                      st.cnt++;
+                    }
+                  }
+                }
+                // a block adds at most 8 keys: keep cnt <= kBufSlots - 8 between blocks
+                if (__any_sync(kFull, st.cnt > kBufSlots - 8)) {
+                  __syncwarp();
+                  warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp);
+                  thr_f = st.thr_key ? score_of_goodness<true>((uint32_t)(st.thr_key >> 32)) : -INFINITY;
+                }
               }
             }
           }

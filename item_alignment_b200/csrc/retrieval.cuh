@@ -29,7 +29,7 @@ template <bool DESC> __device__ __forceinline__ uint64_t make_key(float s, uint3
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kListCap = 128;   // IA_MAX_K: list entries per query (4 per lane)
-constexpr int kBufSlots = 16;   // append-buffer slots per query
+constexpr int kBufSlots = 24;   // append-buffer slots per query
 constexpr int kBufPitch = kBufSlots + 1;  // u64 words per query in shared memory (padded)
 
 // Warp-cooperative merge of up to 32 new keys (one per lane, 0 = none) into a sorted (descending) list of

@@ -8,6 +8,7 @@ q_n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 c_n = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
 d = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
 measure = sys.argv[4] if len(sys.argv) > 4 else "cosine"
+k = int(sys.argv[5]) if len(sys.argv) > 5 else 100
 dev = torch.device("cuda:0")
 gen = torch.Generator(device=dev).manual_seed(1)
 cat = torch.tanh(torch.randn(c_n, d, device=dev, generator=gen)).to(torch.bfloat16)
@@ -16,8 +17,8 @@ with ia.CatalogIndex(cat) as index:
     for _ in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        keys = index.topk_keys(q, 100, measure)
+        keys = index.topk_keys(q, k, measure)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        print(f"{measure} Q={q_n} C={c_n} D={d}: {ms:.2f} ms, {2.0*q_n*c_n*d/ms/1e9:.1f} TFLOP/s, {q_n/ms*1e3:.0f} q/s")
+        print(f"{measure} k={k} Q={q_n} C={c_n} D={d}: {ms:.2f} ms, {2.0*q_n*c_n*d/ms/1e9:.1f} TFLOP/s, {q_n/ms*1e3:.0f} q/s")
