@@ -133,7 +133,9 @@ void ia_catalog_destroy(ia_catalog* cat);
 #define IA_MAX_K 128
 int ia_catalog_topk(ia_catalog* cat, int measure, const void* queries, int64_t q, int64_t ldq,
                     int k, uint64_t* keys_out, ia_stream_t stream);
-/* bytes of device scratch ia_catalog_topk uses internally for (q, k) (allocated lazily, reused) */
+/* Telemetry of the last ia_catalog_topk on this handle (synchronises the device): out8[0] keys appended to the
+ * per-query buffers, [1] buffer->list merges, [2] 32-column groups and [3] 8-column blocks that left the fast path. */
+int ia_catalog_last_stats(ia_catalog* cat, uint64_t* out8);
 /* merge `parts` sorted key lists [parts, q, k] -> [q, k] (after the all-gather of shard results) */
 int ia_topk_merge(const uint64_t* keys_in, int parts, int64_t q, int k, uint64_t* keys_out,
                   ia_stream_t stream);

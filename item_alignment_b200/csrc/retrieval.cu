@@ -34,8 +34,40 @@ struct RetrParams {
   const float* qinv;    // [q_rows]                  (cosine)
   uint64_t* lists;      // [n_splits*n_qt][BM][kListCap]
   uint32_t* tau_global; // [n_qt*BM] best published k-th goodness per query (0 = none)
+  uint32_t* done;       // [n_items*4] set when a warp's quarter of an item's lists is final
+  unsigned long long* stats;  // [8] appends, compactions, rare groups, rare blocks (telemetry)
   uint32_t row_base;    // global row id of catalog row 0 (shard offset)
 };
+
+// A valid lower bound on the final k-th best key of a query from the FINISHED splits of its query tile:
+// if F splits are final and each holds >= r = ceil(k/F) keys >= v (v = the smallest of their r-th best keys),
+// then F*r >= k candidates of disjoint chunks are >= v, so no key <= v can be in the global top-k of the
+// remaining chunks.  As F grows this approaches the k-th best of everything scanned so far.
+__device__ __forceinline__ uint64_t finished_splits_bound(const RetrParams& p, int qt, int my_split, int quarter,
+                                                          int row_local, int tile_rows) {
+  const int lane = threadIdx.x & 31;
+  unsigned fin_lo = 0;   // up to 32 splits tracked (enough: the bound saturates quickly)
+  const int ns = p.n_splits < 32 ? p.n_splits : 32;
+  if (lane < ns && lane != my_split) {
+    const uint32_t* flag = p.done + ((size_t)(lane * p.n_qt + qt)) * 4 + quarter;
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    fin_lo = v != 0;
+  }
+  unsigned fin = __ballot_sync(kFull, fin_lo != 0);
+  const int f = __popc(fin);
+  if (f < 2) return 0ull;            // one finished split gives its k-th best: already in tau_global
+  const int r = (p.k + f - 1) / f;
+  uint64_t bound = ~0ull;
+  while (fin) {
+    const int sp = __ffs(fin) - 1;
+    fin &= fin - 1;
+    const uint64_t* list = p.lists + (((size_t)sp * p.n_qt + qt) * tile_rows + row_local) * kListCap;
+    const uint64_t key = __ldcg(list + (r - 1));
+    bound = key < bound ? key : bound;
+  }
+  return bound;                       // 0 if any finished list is shorter than r: no bound
+}
 
 // =============================================================================== tensor-core kernel
 namespace tc {
@@ -44,7 +76,9 @@ constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTE
 constexpr int THREADS = 192;
 constexpr int BUF_BYTES = BM * kBufPitch * 8;
 constexpr int CINV_BYTES = 2 * BN * 4;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BUF_BYTES + CINV_BYTES + 256 + 1024;  // + barriers + align slack
+constexpr int SCR_BYTES = 4 * kScrWords * 8;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BUF_BYTES + CINV_BYTES + SCR_BYTES + 256 + 1024;  // + barriers + align slack
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 }  // namespace tc
 
 template <bool COSINE, int AB_FORMAT>
@@ -56,19 +90,21 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* buf = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   float* cinv_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BUF_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + BUF_BYTES + CINV_BYTES);
+  uint64_t* scr_all = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + BUF_BYTES + CINV_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + BUF_BYTES + CINV_BYTES + SCR_BYTES);
   uint64_t* full_bar = bars;                // [STAGES] TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;      // [STAGES] MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * STAGES;  // [2] MMA -> epilogue
   uint64_t* tempty_bar = tfull_bar + 2;     // [2] epilogue -> MMA
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* cfull_bar = tempty_bar + 2;     // [2] 1/|c| tile landed (bulk copy issued by the MMA thread)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(cfull_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_c);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); mbar_init(&cfull_bar[a], 1); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, 512);
@@ -110,8 +146,12 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const int t0 = split * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
         for (int t = t0; t < t1; ++t) {
-          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator (and its 1/|c| tile)
           tc_fence_after();
+          if (COSINE) {   // this tile's inverse catalog norms ride along: 1 KB bulk copy, lands long before the MMAs finish
+            mbar_arrive_expect_tx(&cfull_bar[acc], BN * 4);
+            bulk_load_1d(cinv_s + acc * BN, p.cinv + (size_t)t * BN, BN * 4, &cfull_bar[acc]);
+          }
           const uint32_t d_tmem = tmem_base + acc * BN;
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(&full_bar[stage], phase);
@@ -134,8 +174,9 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     // ------------------------------------------------------------------ epilogue: fused normalise + top-k
     const int e = warp & 3;                 // TMEM lane quarter this warp may access
     const int row_local = e * 32 + lane;    // query row inside the tile == TMEM lane
-    const int etid = (warp - 2) * 32 + lane;  // 0..127 among epilogue threads
     uint64_t* buf_warp = buf + (size_t)(e * 32) * kBufPitch;
+    uint64_t* scr = scr_all + (size_t)(warp - 2) * kScrWords;
+    TopKStats stats{0u, 0u, 0u, 0u};
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -151,20 +192,18 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       __syncwarp();
       uint32_t* tau_warp = p.tau_global + qt * BM + e * 32;
       TopKThread st{0ull, 0};
+      st.thr_key = finished_splits_bound(p, qt, split, e, row_local, BM);
 
       for (int t = t0; t < t1; ++t) {
         const int64_t j0 = (int64_t)t * BN;
-        float* cs = cinv_s + acc * BN;
-        if (COSINE) {
-          for (int i = etid; i < BN; i += 128) cs[i] = (j0 + i < p.c_rows) ? __ldg(p.cinv + j0 + i) : 0.f;
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
+        const float* cs = cinv_s + acc * BN;
         {  // pick up what other CTAs have published for this query
           const uint64_t gk = (uint64_t)(*reinterpret_cast<volatile uint32_t*>(tau_warp + lane)) << 32;
           if (gk > st.thr_key) st.thr_key = gk;
         }
         float thr_f = st.thr_key ? score_of_goodness<true>((uint32_t)(st.thr_key >> 32)) : -INFINITY;
 
+        if (COSINE) mbar_wait(&cfull_bar[acc], acc_phase);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + acc * BN;
@@ -195,9 +234,11 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           const float mg = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
           if (__any_sync(kFull, q_ok && mg >= thr_f)) {
             // rare path, per 8-column block, straight from the registers
+            stats.rare_groups++;
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
               if (__any_sync(kFull, q_ok && m8[b] >= thr_f)) {
+                stats.rare_blocks++;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                   const float s = COSINE ? v[8 * b + c] * qinv : v[8 * b + c];
@@ -207,13 +248,14 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                     if (key > st.thr_key) {
                       buf_warp[lane * kBufPitch + st.cnt] = key;
                       st.cnt++;
+                      stats.appends++;
                     }
                   }
                 }
                 // a block adds at most 8 keys: keep cnt <= kBufSlots - 8 between blocks
                 if (__any_sync(kFull, st.cnt > kBufSlots - 8)) {
                   __syncwarp();
-                  warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp);
+                  warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp, scr, stats);
                   thr_f = st.thr_key ? score_of_goodness<true>((uint32_t)(st.thr_key >> 32)) : -INFINITY;
                 }
               }
@@ -226,7 +268,23 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       __syncwarp();
-      warp_compact(st, 1, p.k, buf_warp, lists_warp, tau_warp);   // flush
+      warp_compact(st, 1, p.k, buf_warp, lists_warp, tau_warp, scr, stats);   // flush
+      // publish: this quarter of the item's lists is final (release after every lane's list writes)
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        uint32_t* flag = p.done + (size_t)item * 4 + e;
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(1u) : "memory");
+      }
+    }
+    if (p.stats != nullptr) {
+      const unsigned a = __reduce_add_sync(kFull, stats.appends);
+      if (lane == 0) {
+        atomicAdd(p.stats + 0, (unsigned long long)a);
+        atomicAdd(p.stats + 1, (unsigned long long)stats.compactions);
+        atomicAdd(p.stats + 2, (unsigned long long)stats.rare_groups);
+        atomicAdd(p.stats + 3, (unsigned long long)stats.rare_blocks);
+      }
     }
   }
 
@@ -244,7 +302,7 @@ namespace simt {
 constexpr int BM = 64, BN = 128, BK = 32, THREADS = 256;
 constexpr int QS = BK * (BM + 1), CS = BK * (BN + 1), SS = BM * (BN + 1);
 constexpr int STAGE_FLOATS = (QS + CS) > SS ? (QS + CS) : SS;
-constexpr int SMEM_BYTES = STAGE_FLOATS * 4 + BM * kBufPitch * 8;
+constexpr int SMEM_BYTES = STAGE_FLOATS * 4 + BM * kBufPitch * 8 + 2 * kScrWords * 8;
 }  // namespace simt
 
 template <typename T, int MEASURE>
@@ -258,6 +316,8 @@ retrieve_simt_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__
   float* Cs = Qs + QS;                              // [BK][BN+1]
   float* Ss = reinterpret_cast<float*>(smem_raw);   // [BM][BN+1] (aliases the staging tiles)
   uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw + STAGE_FLOATS * 4);
+  uint64_t* scr = buf + BM * kBufPitch + (size_t)((threadIdx.x >> 5) & 1) * kScrWords;
+  TopKStats stats{0u, 0u, 0u, 0u};
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ty = tid >> 4, tx = tid & 15;
   const int n_items = p.n_qt * p.n_splits;
@@ -277,6 +337,7 @@ retrieve_simt_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__
       for (int i = lane; i < 32 * kListCap; i += 32) lists_warp[i] = 0ull;
       if (MEASURE == IA_COSINE) qinv = (q0 + tid < p.q_rows) ? __ldg(p.qinv + q0 + tid) : 0.f;
       __syncwarp();
+      st.thr_key = finished_splits_bound(p, qt, split, warp, tid, BM);
     }
 
     for (int t = t0; t < t1; ++t) {
@@ -353,7 +414,7 @@ retrieve_simt_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__
           }
           if (__any_sync(kFull, st.cnt == kBufSlots)) {
             __syncwarp();
-            warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp);
+            warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp, scr, stats);
             thr_f = st.thr_key ? score_of_goodness<DESC>((uint32_t)(st.thr_key >> 32)) : (DESC ? -INFINITY : INFINITY);
           }
         }
@@ -361,7 +422,13 @@ retrieve_simt_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__
     }
     if (warp < 2) {
       __syncwarp();
-      warp_compact(st, 1, p.k, buf_warp, lists_warp, tau_warp);
+      warp_compact(st, 1, p.k, buf_warp, lists_warp, tau_warp, scr, stats);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        uint32_t* flag = p.done + (size_t)item * 4 + warp;
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(1u) : "memory");
+      }
     }
   }
 }
@@ -374,8 +441,10 @@ __global__ void __launch_bounds__(256) merge_lists_kernel(const uint64_t* __rest
                                                           int n_qt, int tile_rows, int src_len, int k,
                                                           uint64_t* __restrict__ out) {
   __shared__ uint64_t work[8][kListCap];
+  __shared__ uint64_t scratch[8][kScrWords];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t* list = work[warp];
+  uint64_t* scr = scratch[warp];
   for (int64_t q = (int64_t)blockIdx.x * 8 + warp; q < q_rows; q += (int64_t)gridDim.x * 8) {
     for (int i = lane; i < kListCap; i += 32) list[i] = 0ull;
     __syncwarp();
@@ -389,10 +458,8 @@ __global__ void __launch_bounds__(256) merge_lists_kernel(const uint64_t* __rest
         // sorted descending: once the batch's best key cannot enter the list, the rest of this part cannot either
         const uint64_t head = __shfl_sync(kFull, bk, 0);
         if (head == 0 || (kth != 0 && head < kth)) break;
-        uint64_t Lr[4];
-        warp_load_list(Lr, list);
-        __syncwarp();
-        kth = warp_merge_keys(Lr, bk, k, list);
+        const int c = __popc(__ballot_sync(kFull, bk != 0));
+        kth = warp_merge_keys(list, bk, c, k, scr);
       }
     }
     __syncwarp();
@@ -476,8 +543,9 @@ struct ia_catalog {
   CUtensorMap tmap_c;
   // lazily grown scratch
   uint64_t* lists; size_t lists_bytes;
-  uint32_t* tau; size_t tau_bytes;
+  uint32_t* tau; size_t tau_bytes;      // [tau | done flags]
   float* qinv; size_t qinv_bytes;
+  unsigned long long* stats;            // [8]
 };
 
 static int grow(void** ptr, size_t* have, size_t need) {
@@ -522,11 +590,15 @@ int ia_catalog_create(ia_catalog** out, int dtype, const void* catalog, int64_t 
   if (!cat) { set_error("out of host memory"); return IA_ERR_CUDA; }
   cat->dtype = dtype; cat->data = catalog; cat->c = c; cat->d = d; cat->ld = ld; cat->row_base = (uint32_t)row_base;
   cat->lists = nullptr; cat->lists_bytes = 0; cat->tau = nullptr; cat->tau_bytes = 0; cat->qinv = nullptr; cat->qinv_bytes = 0;
-  cat->cinv = nullptr; cat->tc_ok = false;
+  cat->cinv = nullptr; cat->tc_ok = false; cat->stats = nullptr;
   cudaGetDevice(&cat->device);
-  cudaError_t e = cudaMalloc(&cat->cinv, sizeof(float) * (size_t)c);
-  if (e != cudaSuccess) { set_error("cudaMalloc(cinv) failed: %s", cudaGetErrorString(e)); delete cat; return IA_ERR_CUDA; }
   cudaStream_t s = (cudaStream_t)stream;
+  // inverse norms padded with zeros to whole 256-row tiles: the kernel bulk-copies one tile's worth at a time
+  const size_t cinv_n = ((size_t)c + tc::BN - 1) / tc::BN * tc::BN;
+  cudaError_t e = cudaMalloc(&cat->cinv, sizeof(float) * cinv_n);
+  if (e == cudaSuccess) e = cudaMalloc(&cat->stats, sizeof(unsigned long long) * 8);
+  if (e == cudaSuccess) e = cudaMemsetAsync(cat->cinv, 0, sizeof(float) * cinv_n, s);
+  if (e != cudaSuccess) { set_error("catalog allocation failed: %s", cudaGetErrorString(e)); if (cat->cinv) cudaFree(cat->cinv); delete cat; return IA_ERR_CUDA; }
   const int64_t want = (c + 7) / 8;
   const int grid = (int)(want < 8 * sm_count() ? want : 8 * sm_count());
   if (dtype == IA_F32) inv_norm_rows_kernel<float><<<grid, 256, 0, s>>>((const float*)catalog, c, (int)d, ld, kCosEps, cat->cinv);
@@ -548,6 +620,7 @@ void ia_catalog_destroy(ia_catalog* cat) {
   if (cat->lists) cudaFree(cat->lists);
   if (cat->tau) cudaFree(cat->tau);
   if (cat->qinv) cudaFree(cat->qinv);
+  if (cat->stats) cudaFree(cat->stats);
   delete cat;
 }
 
@@ -579,9 +652,11 @@ int ia_catalog_topk(ia_catalog* cat, int measure, const void* queries, int64_t q
 
   int rc;
   if ((rc = grow((void**)&cat->lists, &cat->lists_bytes, sizeof(uint64_t) * (size_t)n_items * BM * kListCap)) != IA_OK) return rc;
-  if ((rc = grow((void**)&cat->tau, &cat->tau_bytes, sizeof(uint32_t) * (size_t)p.n_qt * BM)) != IA_OK) return rc;
-  IA_CUDA_CHECK(cudaMemsetAsync(cat->tau, 0, sizeof(uint32_t) * (size_t)p.n_qt * BM, s));
-  p.lists = cat->lists; p.tau_global = cat->tau; p.cinv = cat->cinv;
+  const size_t tau_n = (size_t)p.n_qt * BM, done_n = (size_t)n_items * 4;
+  if ((rc = grow((void**)&cat->tau, &cat->tau_bytes, sizeof(uint32_t) * (tau_n + done_n))) != IA_OK) return rc;
+  IA_CUDA_CHECK(cudaMemsetAsync(cat->tau, 0, sizeof(uint32_t) * (tau_n + done_n), s));
+  IA_CUDA_CHECK(cudaMemsetAsync(cat->stats, 0, sizeof(unsigned long long) * 8, s));
+  p.lists = cat->lists; p.tau_global = cat->tau; p.done = cat->tau + tau_n; p.cinv = cat->cinv; p.stats = cat->stats;
   if (measure == IA_COSINE) {
     if ((rc = grow((void**)&cat->qinv, &cat->qinv_bytes, sizeof(float) * (size_t)q)) != IA_OK) return rc;
     if ((rc = ia_row_inv_norm(cat->dtype, queries, q, cat->d, ldq, kCosEps, cat->qinv, stream)) != IA_OK) return rc;
@@ -625,6 +700,12 @@ int ia_catalog_topk(ia_catalog* cat, int measure, const void* queries, int64_t q
   const int mgrid = (int)(mwant < 4 * sms ? mwant : 4 * sms);
   merge_lists_kernel<<<mgrid, 256, 0, s>>>(cat->lists, p.n_splits, q, p.n_qt, BM, kListCap, k, keys_out);
   IA_LAUNCH_CHECK();
+  return IA_OK;
+}
+
+int ia_catalog_last_stats(ia_catalog* cat, uint64_t* out8) {
+  if (cat == nullptr || out8 == nullptr) { set_error("bad arguments"); return IA_ERR_INVALID; }
+  IA_CUDA_CHECK(cudaMemcpy(out8, cat->stats, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost));   // synchronising
   return IA_OK;
 }
 

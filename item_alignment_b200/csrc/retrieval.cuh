@@ -32,33 +32,48 @@ constexpr int kListCap = 128;   // IA_MAX_K: list entries per query (4 per lane)
 constexpr int kBufSlots = 24;   // append-buffer slots per query
 constexpr int kBufPitch = kBufSlots + 1;  // u64 words per query in shared memory (padded)
 
-// Warp-cooperative merge of up to 32 new keys (one per lane, 0 = none) into a sorted (descending) list of
-// <= 128 keys held 4 per lane: Lr[r] is position lane + 32*r.  Rank based: every existing entry moves down
-// by the number of new keys larger than it, every new key lands at (#list entries larger) + (#new keys
-// larger).  Writes the first k positions to `list` and returns the key at position k-1 (0 if the merged
-// list is shorter than k) to all lanes.
-__device__ __forceinline__ uint64_t warp_merge_keys(const uint64_t (&Lr)[4], uint64_t bk, int k, uint64_t* list) {
+constexpr int kScrWords = kListCap + 32;   // per-warp shared scratch of the merge: staged list + new keys
+
+// Warp-cooperative merge of up to 32 new keys (one per lane, 0 = none; lanes 0..c-1 hold them) into a sorted
+// (descending) list of <= 128 keys in global memory.  Rank based, every lane works in parallel:
+//   new key : position = (#list entries larger, binary search in the staged list)
+//                      + (#new keys larger, c broadcast compares)
+//   list entry at p : moves down by #new keys larger (binary search in the sorted new keys)
+// Writes the first k positions back to `list`, returns the key at position k-1 (0 if the merged list is
+// shorter than k) to all lanes.  scr: kScrWords u64 of shared memory owned by this warp.
+__device__ __forceinline__ uint64_t warp_merge_keys(uint64_t* list, uint64_t bk, int c, int k, uint64_t* scr) {
   const int lane = threadIdx.x & 31;
-  int shift0 = 0, shift1 = 0, shift2 = 0, shift3 = 0, mypos = 0;
-  unsigned has = __ballot_sync(kFull, bk != 0);
-  while (has) {
-    const int t = __ffs(has) - 1;
-    has &= has - 1;
-    const uint64_t b = __shfl_sync(kFull, bk, t);
-    const bool g0 = Lr[0] > b, g1 = Lr[1] > b, g2 = Lr[2] > b, g3 = Lr[3] > b;
-    int cnt = __popc(__ballot_sync(kFull, g0)) + __popc(__ballot_sync(kFull, g1)) +
-              __popc(__ballot_sync(kFull, g2)) + __popc(__ballot_sync(kFull, g3)) +
-              __popc(__ballot_sync(kFull, bk > b));
-    shift0 += !g0; shift1 += !g1; shift2 += !g2; shift3 += !g3;
-    if (lane == t) mypos = cnt;
+  uint64_t Lr[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    Lr[r] = list[lane + 32 * r];
+    scr[lane + 32 * r] = Lr[r];
   }
+  scr[kListCap + lane] = bk;
+  __syncwarp();
+  int rank_b = 0;
+  for (int i = 0; i < c; ++i) rank_b += (scr[kListCap + i] > bk);
+  int lo = 0, hi = kListCap;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {          // answers 0..128: 8 halvings; empty (0) tail entries are < any key
+    const int mid = (lo + hi) >> 1;
+    if (lo < hi) { if (scr[mid] > bk) lo = mid + 1; else hi = mid; }
+  }
+  const int mypos = lo + rank_b;
+  __syncwarp();
+  if (bk != 0) scr[kListCap + rank_b] = bk;   // new keys sorted descending (keys are unique)
   __syncwarp();
   uint64_t kth = 0;
-  const int sh[4] = {shift0, shift1, shift2, shift3};
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     if (Lr[r] != 0) {
-      const int p = lane + 32 * r + sh[r];
+      int l2 = 0, h2 = c;
+#pragma unroll
+      for (int it = 0; it < 6; ++it) {       // answers 0..c, c <= 32: 6 halvings
+        const int mid = (l2 + h2) >> 1;
+        if (l2 < h2) { if (scr[kListCap + mid] > Lr[r]) l2 = mid + 1; else h2 = mid; }
+      }
+      const int p = lane + 32 * r + l2;
       if (p < k) {
         list[p] = Lr[r];
         if (p == k - 1) kth = Lr[r];
@@ -70,31 +85,30 @@ __device__ __forceinline__ uint64_t warp_merge_keys(const uint64_t (&Lr)[4], uin
     if (mypos == k - 1) kth = bk;
   }
   __syncwarp();
-  const uint32_t lo = __reduce_or_sync(kFull, (uint32_t)kth);
-  const uint32_t hi = __reduce_or_sync(kFull, (uint32_t)(kth >> 32));
-  return ((uint64_t)hi << 32) | lo;
-}
-
-__device__ __forceinline__ void warp_load_list(uint64_t (&Lr)[4], const uint64_t* list) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int r = 0; r < 4; ++r) Lr[r] = list[lane + 32 * r];
+  const uint32_t klo = __reduce_or_sync(kFull, (uint32_t)kth);
+  const uint32_t khi = __reduce_or_sync(kFull, (uint32_t)(kth >> 32));
+  return ((uint64_t)khi << 32) | klo;
 }
 
 // Streaming top-k state of ONE query, owned by one thread; 32 queries (one warp) are compacted together.
-//   thr_key : candidates must beat this key (max of the local k-th best key and the k-th best goodness any
-//             other CTA has published for this query, tau_global)
+//   thr_key : candidates must beat this key (max of the local k-th best key and the bounds other CTAs
+//             published for this query)
 //   cnt     : filled slots of this query's append buffer (shared memory, kBufPitch u64 per query)
 struct TopKThread {
   uint64_t thr_key;
   int cnt;
 };
 
+struct TopKStats {
+  unsigned appends, compactions, rare_groups, rare_blocks;
+};
+
 // Compact the append buffers of every lane whose buffer holds >= min_cnt keys into its global list.
 // buf_warp: this warp's 32 append buffers; lists_warp: this warp's 32 lists (kListCap u64 each).
 // Must be called by all 32 lanes.  tau_global may be null.
 __device__ __forceinline__ void warp_compact(TopKThread& st, int min_cnt, int k, uint64_t* buf_warp,
-                                             uint64_t* lists_warp, uint32_t* tau_global_warp) {
+                                             uint64_t* lists_warp, uint32_t* tau_global_warp, uint64_t* scr,
+                                             TopKStats& stats) {
   const int lane = threadIdx.x & 31;
   unsigned need = __ballot_sync(kFull, st.cnt >= min_cnt && st.cnt > 0);
   while (need) {
@@ -102,10 +116,9 @@ __device__ __forceinline__ void warp_compact(TopKThread& st, int min_cnt, int k,
     need &= need - 1;
     const int c = __shfl_sync(kFull, st.cnt, ql);
     uint64_t* list = lists_warp + (size_t)ql * kListCap;
-    uint64_t Lr[4];
-    warp_load_list(Lr, list);
     const uint64_t bk = lane < c ? buf_warp[ql * kBufPitch + lane] : 0ull;
-    const uint64_t kth = warp_merge_keys(Lr, bk, k, list);
+    const uint64_t kth = warp_merge_keys(list, bk, c, k, scr);
+    stats.compactions++;
     if (lane == ql) {
       st.cnt = 0;
       if (kth > st.thr_key) st.thr_key = kth;
@@ -157,6 +170,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// 1-D bulk copy global -> shared with mbarrier completion (SASS: UBLKCP); 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");

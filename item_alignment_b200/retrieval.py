@@ -81,6 +81,12 @@ class CatalogIndex:
         """(scores [Q,k] fp32, rows [Q,k] int64 global ids), best first; -1 / +-inf where fewer than k rows exist."""
         return unpack_keys(self.topk_keys(queries, k, measure), measure)
 
+    def last_stats(self):
+        """Telemetry of the last topk call (synchronises): appended keys, merges, rare groups, rare blocks."""
+        out = (ctypes.c_uint64 * 8)()
+        check(lib().ia_catalog_last_stats(self._h, out))
+        return dict(appends=out[0], compactions=out[1], rare_groups=out[2], rare_blocks=out[3])
+
 
 def unpack_keys(keys, measure):
     descending = measure in ("inner_product", "cosine")

@@ -21,4 +21,6 @@ with ia.CatalogIndex(cat) as index:
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
+        st = index.last_stats()
+        print(f"   stats per query: appends {st['appends']/q_n:.0f} compactions {st['compactions']/q_n:.1f}; rare groups {st['rare_groups']} blocks {st['rare_blocks']}")
         print(f"{measure} k={k} Q={q_n} C={c_n} D={d}: {ms:.2f} ms, {2.0*q_n*c_n*d/ms/1e9:.1f} TFLOP/s, {q_n/ms*1e3:.0f} q/s")
