@@ -69,6 +69,28 @@ __device__ __forceinline__ uint64_t finished_splits_bound(const RetrParams& p, i
   return bound;                       // 0 if any finished list is shorter than r: no bound
 }
 
+// v[c] for a runtime c in [0,32): binary select tree (31 SEL), registers stay registers
+__device__ __forceinline__ float select32(const float (&v)[32], int c) {
+  float a[16], b8[8], c4[4], d2[2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (c & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b8[i] = (c & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c4[i] = (c & 4) ? b8[2 * i + 1] : b8[2 * i];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) d2[i] = (c & 8) ? c4[2 * i + 1] : c4[2 * i];
+  return (c & 16) ? d2[1] : d2[0];
+}
+
+// Largest-safe pre-filter threshold t' with:  (x * qinv >= thr)  =>  (x >= t')  for every float x, qinv > 0.
+// t' = thr / qinv pulled down by 4 ulp-ish relative steps; -inf stays -inf.  qinv == 0 (padded query) -> +inf.
+__device__ __forceinline__ float prefilter_threshold(float thr, float qinv) {
+  if (!(qinv > 0.f)) return INFINITY;
+  const float t = thr / qinv;
+  return t - fabsf(t) * 4.8e-7f - 1e-37f;
+}
+
 // =============================================================================== tensor-core kernel
 namespace tc {
 constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
@@ -87,7 +109,8 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                    const RetrParams p) {
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment for the 128B-swizzled operand tiles, keeping the pointer's shared-memory provenance
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* buf = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   float* cinv_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BUF_BYTES);
   uint64_t* scr_all = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + BUF_BYTES + CINV_BYTES);
@@ -207,57 +230,64 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + acc * BN;
+        // pre-filter threshold in the (acc * 1/|c|) domain: a hair below thr_f / (1/|q|) so that rounding can only
+        // let extra candidates through; the exact test on (acc * 1/|c|) * 1/|q| follows in the rare path
+        float thr_pre = thr_f;
+        if (COSINE) thr_pre = prefilter_threshold(thr_f, qinv);
 #pragma unroll 1
         for (int g = 0; g < BN / 32; ++g) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + g * 32, r);
           tmem_ld_wait();
-          // fast path: scale by 1/|c| and take the maximum of each 8-column block (2-3 instructions per score)
-          float v[32], m8[4];
+          // fast path: scale by 1/|c| and build this thread's 32-bit hit mask (3 instructions per score)
+          float v[32];
+          unsigned mask = 0;
           const float4* cs4 = reinterpret_cast<const float4*>(cs + g * 32);
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int c = 8 * b + 4 * h;
-              v[c + 0] = __uint_as_float(r[c + 0]); v[c + 1] = __uint_as_float(r[c + 1]);
-              v[c + 2] = __uint_as_float(r[c + 2]); v[c + 3] = __uint_as_float(r[c + 3]);
-              if (COSINE) {
-                const float4 ci = cs4[2 * b + h];
-                v[c + 0] *= ci.x; v[c + 1] *= ci.y; v[c + 2] *= ci.z; v[c + 3] *= ci.w;
-              }
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const int c = 4 * c4;
+            v[c + 0] = __uint_as_float(r[c + 0]); v[c + 1] = __uint_as_float(r[c + 1]);
+            v[c + 2] = __uint_as_float(r[c + 2]); v[c + 3] = __uint_as_float(r[c + 3]);
+            if (COSINE) {
+              const float4 ci = cs4[c4];
+              v[c + 0] *= ci.x; v[c + 1] *= ci.y; v[c + 2] *= ci.z; v[c + 3] *= ci.w;
             }
-            m8[b] = fmaxf(fmaxf(fmaxf(v[8 * b], v[8 * b + 1]), fmaxf(v[8 * b + 2], v[8 * b + 3])),
-                          fmaxf(fmaxf(v[8 * b + 4], v[8 * b + 5]), fmaxf(v[8 * b + 6], v[8 * b + 7])));
-            if (COSINE) m8[b] *= qinv;     // x (1/|q|) > 0 is monotone: max commutes with it exactly
+            mask |= (v[c + 0] >= thr_pre ? 1u : 0u) << (c + 0);
+            mask |= (v[c + 1] >= thr_pre ? 1u : 0u) << (c + 1);
+            mask |= (v[c + 2] >= thr_pre ? 1u : 0u) << (c + 2);
+            mask |= (v[c + 3] >= thr_pre ? 1u : 0u) << (c + 3);
           }
-          const float mg = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
-          if (__any_sync(kFull, q_ok && mg >= thr_f)) {
-            // rare path, per 8-column block, straight from the registers
+          if (!q_ok) mask = 0;
+          if (__any_sync(kFull, mask != 0)) {
             stats.rare_groups++;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              if (__any_sync(kFull, q_ok && m8[b] >= thr_f)) {
-                stats.rare_blocks++;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                  const float s = COSINE ? v[8 * b + c] * qinv : v[8 * b + c];
-                  const int64_t j = j0 + g * 32 + 8 * b + c;
-                  if (q_ok && s >= thr_f && j < p.c_rows) {
-                    const uint64_t key = make_key<true>(s, p.row_base + (uint32_t)j);
-                    if (key > st.thr_key) {
-                      buf_warp[lane * kBufPitch + st.cnt] = key;
-                      st.cnt++;
-                      stats.appends++;
-                    }
+            // rare path: every lane walks its own hits (usually one), all lanes in parallel
+            while (__any_sync(kFull, mask != 0)) {
+              stats.rare_blocks++;
+              if (mask != 0) {
+                const int c = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float vc = select32(v, c);
+                const float s = COSINE ? vc * qinv : vc;
+                const int64_t j = j0 + g * 32 + c;
+                if (s >= thr_f && j < p.c_rows) {
+                  const uint64_t key = make_key<true>(s, p.row_base + (uint32_t)j);
+                  if (key > st.thr_key) {
+                    buf_warp[lane * kBufPitch + st.cnt] = key;
+                    st.cnt++;
+                    stats.appends++;
                   }
                 }
-                // a block adds at most 8 keys: keep cnt <= kBufSlots - 8 between blocks
-                if (__any_sync(kFull, st.cnt > kBufSlots - 8)) {
-                  __syncwarp();
-                  warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp, scr, stats);
-                  thr_f = st.thr_key ? score_of_goodness<true>((uint32_t)(st.thr_key >> 32)) : -INFINITY;
-                }
+              }
+              if (__any_sync(kFull, st.cnt == kBufSlots)) {
+                __syncwarp();
+                warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp, scr, stats);
+                thr_f = st.thr_key ? score_of_goodness<true>((uint32_t)(st.thr_key >> 32)) : -INFINITY;
+                thr_pre = COSINE ? prefilter_threshold(thr_f, qinv) : thr_f;
+                // drop hits the tighter threshold already rules out
+                unsigned m2 = 0;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) m2 |= (v[c] >= thr_pre ? 1u : 0u) << c;
+                mask &= m2;
               }
             }
           }

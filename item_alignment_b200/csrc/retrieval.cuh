@@ -41,14 +41,17 @@ constexpr int kScrWords = kListCap + 32;   // per-warp shared scratch of the mer
 //   list entry at p : moves down by #new keys larger (binary search in the sorted new keys)
 // Writes the first k positions back to `list`, returns the key at position k-1 (0 if the merged list is
 // shorter than k) to all lanes.  scr: kScrWords u64 of shared memory owned by this warp.
-__device__ __forceinline__ uint64_t warp_merge_keys(uint64_t* list, uint64_t bk, int c, int k, uint64_t* scr) {
+__device__ __forceinline__ void warp_load_list(uint64_t (&Lr)[4], const uint64_t* list) {
   const int lane = threadIdx.x & 31;
-  uint64_t Lr[4];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    Lr[r] = list[lane + 32 * r];
-    scr[lane + 32 * r] = Lr[r];
-  }
+  for (int r = 0; r < 4; ++r) Lr[r] = list[lane + 32 * r];
+}
+
+__device__ __forceinline__ uint64_t warp_merge_loaded(const uint64_t (&Lr)[4], uint64_t* list, uint64_t bk, int c, int k,
+                                                      uint64_t* scr) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) scr[lane + 32 * r] = Lr[r];
   scr[kListCap + lane] = bk;
   __syncwarp();
   int rank_b = 0;
@@ -90,6 +93,12 @@ __device__ __forceinline__ uint64_t warp_merge_keys(uint64_t* list, uint64_t bk,
   return ((uint64_t)khi << 32) | klo;
 }
 
+__device__ __forceinline__ uint64_t warp_merge_keys(uint64_t* list, uint64_t bk, int c, int k, uint64_t* scr) {
+  uint64_t Lr[4];
+  warp_load_list(Lr, list);
+  return warp_merge_loaded(Lr, list, bk, c, k, scr);
+}
+
 // Streaming top-k state of ONE query, owned by one thread; 32 queries (one warp) are compacted together.
 //   thr_key : candidates must beat this key (max of the local k-th best key and the bounds other CTAs
 //             published for this query)
@@ -106,18 +115,24 @@ struct TopKStats {
 // Compact the append buffers of every lane whose buffer holds >= min_cnt keys into its global list.
 // buf_warp: this warp's 32 append buffers; lists_warp: this warp's 32 lists (kListCap u64 each).
 // Must be called by all 32 lanes.  tau_global may be null.
-__device__ __forceinline__ void warp_compact(TopKThread& st, int min_cnt, int k, uint64_t* buf_warp,
-                                             uint64_t* lists_warp, uint32_t* tau_global_warp, uint64_t* scr,
-                                             TopKStats& stats) {
+// One copy in the binary (noinline): it is called from several places of hot loops whose code must stay
+// inside the instruction cache.  The next lane's list is prefetched from L2 while the current one is merged.
+__device__ __noinline__ void warp_compact(TopKThread& st, int min_cnt, int k, uint64_t* buf_warp,
+                                          uint64_t* lists_warp, uint32_t* tau_global_warp, uint64_t* scr,
+                                          TopKStats& stats) {
   const int lane = threadIdx.x & 31;
   unsigned need = __ballot_sync(kFull, st.cnt >= min_cnt && st.cnt > 0);
+  uint64_t Lnext[4] = {0, 0, 0, 0};
+  if (need) warp_load_list(Lnext, lists_warp + (size_t)(__ffs(need) - 1) * kListCap);
   while (need) {
     const int ql = __ffs(need) - 1;
     need &= need - 1;
     const int c = __shfl_sync(kFull, st.cnt, ql);
     uint64_t* list = lists_warp + (size_t)ql * kListCap;
     const uint64_t bk = lane < c ? buf_warp[ql * kBufPitch + lane] : 0ull;
-    const uint64_t kth = warp_merge_keys(list, bk, c, k, scr);
+    uint64_t Lr[4] = {Lnext[0], Lnext[1], Lnext[2], Lnext[3]};
+    if (need) warp_load_list(Lnext, lists_warp + (size_t)(__ffs(need) - 1) * kListCap);
+    const uint64_t kth = warp_merge_loaded(Lr, list, bk, c, k, scr);
     stats.compactions++;
     if (lane == ql) {
       st.cnt = 0;
