@@ -117,9 +117,16 @@ struct TopKStats {
 // Must be called by all 32 lanes.  tau_global may be null.
 // One copy in the binary (noinline): it is called from several places of hot loops whose code must stay
 // inside the instruction cache.  The next lane's list is prefetched from L2 while the current one is merged.
-__device__ __noinline__ void warp_compact(TopKThread& st, int min_cnt, int k, uint64_t* buf_warp,
-                                          uint64_t* lists_warp, uint32_t* tau_global_warp, uint64_t* scr,
-                                          TopKStats& stats) {
+// State travels by value (registers): references would force the caller's hot state through local memory.
+struct CompactResult {
+  uint64_t thr_key;
+  int cnt;
+  unsigned merges;
+};
+__device__ __noinline__ CompactResult warp_compact_impl(uint64_t thr_key, int cnt, int min_cnt, int k, uint64_t* buf_warp,
+                                                        uint64_t* lists_warp, uint32_t* tau_global_warp, uint64_t* scr) {
+  TopKThread st{thr_key, cnt};
+  TopKStats stats{0u, 0u, 0u, 0u};
   const int lane = threadIdx.x & 31;
   unsigned need = __ballot_sync(kFull, st.cnt >= min_cnt && st.cnt > 0);
   uint64_t Lnext[4] = {0, 0, 0, 0};
@@ -141,6 +148,14 @@ __device__ __noinline__ void warp_compact(TopKThread& st, int min_cnt, int k, ui
     }
   }
   __syncwarp();
+  return CompactResult{st.thr_key, st.cnt, stats.compactions};
+}
+__device__ __forceinline__ void warp_compact(TopKThread& st, int min_cnt, int k, uint64_t* buf_warp, uint64_t* lists_warp,
+                                             uint32_t* tau_global_warp, uint64_t* scr, TopKStats& stats) {
+  const CompactResult r = warp_compact_impl(st.thr_key, st.cnt, min_cnt, k, buf_warp, lists_warp, tau_global_warp, scr);
+  st.thr_key = r.thr_key;
+  st.cnt = r.cnt;
+  stats.compactions += r.merges;
 }
 
 // ------------------------------------------------------------------------------------ PTX wrappers
