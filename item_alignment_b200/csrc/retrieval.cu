@@ -220,15 +220,16 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       for (int t = t0; t < t1; ++t) {
         const int64_t j0 = (int64_t)t * BN;
         const float* cs = cinv_s + acc * BN;
-        {  // pick up what other CTAs have published for this query
-          const uint64_t gk = (uint64_t)(*reinterpret_cast<volatile uint32_t*>(tau_warp + lane)) << 32;
-          if (gk > st.thr_key) st.thr_key = gk;
-        }
-        float thr_f = st.thr_key ? score_of_goodness<true>((uint32_t)(st.thr_key >> 32)) : -INFINITY;
-
+        // what other CTAs have published for this query: issue the (L2-latency) load now, consume it after the waits
+        const uint32_t tau_seen = *reinterpret_cast<volatile uint32_t*>(tau_warp + lane);
         if (COSINE) mbar_wait(&cfull_bar[acc], acc_phase);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
+        {
+          const uint64_t gk = (uint64_t)tau_seen << 32;
+          if (gk > st.thr_key) st.thr_key = gk;
+        }
+        float thr_f = st.thr_key ? score_of_goodness<true>((uint32_t)(st.thr_key >> 32)) : -INFINITY;
         const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + acc * BN;
         // pre-filter threshold in the (acc * 1/|c|) domain: a hair below thr_f / (1/|q|) so that rounding can only
         // let extra candidates through; the exact test on (acc * 1/|c|) * 1/|q| follows in the rare path

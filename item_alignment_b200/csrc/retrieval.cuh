@@ -47,36 +47,55 @@ __device__ __forceinline__ void warp_load_list(uint64_t (&Lr)[4], const uint64_t
   for (int r = 0; r < 4; ++r) Lr[r] = list[lane + 32 * r];
 }
 
+// MAXC: compile-time bound on c (24 from the append buffers, 32 in the list-merge kernel).
+// Everything is written as short independent instruction streams (broadcast shared-memory loads + compares),
+// not dependent chains: one warp per scheduler runs this, so latency, not issue rate, is what it costs.
+template <int MAXC>
 __device__ __forceinline__ uint64_t warp_merge_loaded(const uint64_t (&Lr)[4], uint64_t* list, uint64_t bk, int c, int k,
                                                       uint64_t* scr) {
   const int lane = threadIdx.x & 31;
+  uint32_t* scr32 = reinterpret_cast<uint32_t*>(scr + kListCap);   // reused for the insertion points below
 #pragma unroll
   for (int r = 0; r < 4; ++r) scr[lane + 32 * r] = Lr[r];
   scr[kListCap + lane] = bk;
   __syncwarp();
+  // (1) rank among the new keys: #new keys larger than mine
   int rank_b = 0;
-  for (int i = 0; i < c; ++i) rank_b += (scr[kListCap + i] > bk);
-  int lo = 0, hi = kListCap;
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {          // answers 0..128: 8 halvings; empty (0) tail entries are < any key
-    const int mid = (lo + hi) >> 1;
-    if (lo < hi) { if (scr[mid] > bk) lo = mid + 1; else hi = mid; }
+  for (int i = 0; i < MAXC; ++i) rank_b += (i < c && scr[kListCap + i] > bk) ? 1 : 0;
+  // (2) insertion point in the list = #list entries larger than mine: 8 pivots (every 16th entry), then the
+  //     16 entries of the pivot's segment -- two rounds of independent loads instead of an 8-step search
+  int seg = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) seg += (scr[16 * i + 15] > bk) ? 1 : 0;   // segments entirely larger than my key
+  int lo = 16 * seg;
+  if (seg < 8) {
+    const uint64_t* sp = scr + 16 * seg;
+    int in = 0;
+#pragma unroll
+    for (int i = 0; i < 15; ++i) in += (sp[i] > bk) ? 1 : 0;             // entry 15 of the segment is <= my key
+    lo += in;
   }
   const int mypos = lo + rank_b;
   __syncwarp();
-  if (bk != 0) scr[kListCap + rank_b] = bk;   // new keys sorted descending (keys are unique)
+  // (3) publish insertion points; a list entry at position p moves down by #new keys with insertion point <= p
+  if (lane < c) scr32[lane] = (uint32_t)lo;
   __syncwarp();
+  int sh0 = 0, sh1 = 0, sh2 = 0, sh3 = 0;
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    const int li = (i < c) ? (int)scr32[i] : 0x7fffffff;
+    sh0 += (li <= lane) ? 1 : 0;
+    sh1 += (li <= lane + 32) ? 1 : 0;
+    sh2 += (li <= lane + 64) ? 1 : 0;
+    sh3 += (li <= lane + 96) ? 1 : 0;
+  }
+  const int sh[4] = {sh0, sh1, sh2, sh3};
   uint64_t kth = 0;
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     if (Lr[r] != 0) {
-      int l2 = 0, h2 = c;
-#pragma unroll
-      for (int it = 0; it < 6; ++it) {       // answers 0..c, c <= 32: 6 halvings
-        const int mid = (l2 + h2) >> 1;
-        if (l2 < h2) { if (scr[kListCap + mid] > Lr[r]) l2 = mid + 1; else h2 = mid; }
-      }
-      const int p = lane + 32 * r + l2;
+      const int p = lane + 32 * r + sh[r];
       if (p < k) {
         list[p] = Lr[r];
         if (p == k - 1) kth = Lr[r];
@@ -96,7 +115,7 @@ __device__ __forceinline__ uint64_t warp_merge_loaded(const uint64_t (&Lr)[4], u
 __device__ __forceinline__ uint64_t warp_merge_keys(uint64_t* list, uint64_t bk, int c, int k, uint64_t* scr) {
   uint64_t Lr[4];
   warp_load_list(Lr, list);
-  return warp_merge_loaded(Lr, list, bk, c, k, scr);
+  return warp_merge_loaded<32>(Lr, list, bk, c, k, scr);
 }
 
 // Streaming top-k state of ONE query, owned by one thread; 32 queries (one warp) are compacted together.
@@ -139,7 +158,7 @@ __device__ __noinline__ CompactResult warp_compact_impl(uint64_t thr_key, int cn
     const uint64_t bk = lane < c ? buf_warp[ql * kBufPitch + lane] : 0ull;
     uint64_t Lr[4] = {Lnext[0], Lnext[1], Lnext[2], Lnext[3]};
     if (need) warp_load_list(Lnext, lists_warp + (size_t)(__ffs(need) - 1) * kListCap);
-    const uint64_t kth = warp_merge_loaded(Lr, list, bk, c, k, scr);
+    const uint64_t kth = warp_merge_loaded<kBufSlots>(Lr, list, bk, c, k, scr);
     stats.compactions++;
     if (lane == ql) {
       st.cnt = 0;
