@@ -13,6 +13,7 @@
 //    on the same queries share their k-th best through tau_global so thresholds tighten across splits.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <new>
 
@@ -37,6 +38,8 @@ struct RetrParams {
   uint32_t* done;       // [n_items*4] set when a warp's quarter of an item's lists is final
   unsigned long long* stats;  // [8] appends, compactions, rare groups, rare blocks (telemetry)
   uint32_t row_base;    // global row id of catalog row 0 (shard offset)
+  int flags;            // tuning switches for in-run A/B measurements (env IA_RETR_FLAGS): bit0 merge variant,
+                        // bit1 early tau load, bit2 finished-split bound
 };
 
 // A valid lower bound on the final k-th best key of a query from the FINISHED splits of its query tile:
@@ -215,16 +218,18 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       __syncwarp();
       uint32_t* tau_warp = p.tau_global + qt * BM + e * 32;
       TopKThread st{0ull, 0};
-      st.thr_key = finished_splits_bound(p, qt, split, e, row_local, BM);
+      if (p.flags & 4) st.thr_key = finished_splits_bound(p, qt, split, e, row_local, BM);
 
       for (int t = t0; t < t1; ++t) {
         const int64_t j0 = (int64_t)t * BN;
         const float* cs = cinv_s + acc * BN;
         // what other CTAs have published for this query: issue the (L2-latency) load now, consume it after the waits
-        const uint32_t tau_seen = *reinterpret_cast<volatile uint32_t*>(tau_warp + lane);
+        uint32_t tau_seen = 0;
+        if (p.flags & 2) tau_seen = *reinterpret_cast<volatile uint32_t*>(tau_warp + lane);
         if (COSINE) mbar_wait(&cfull_bar[acc], acc_phase);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
+        if (!(p.flags & 2)) tau_seen = *reinterpret_cast<volatile uint32_t*>(tau_warp + lane);
         {
           const uint64_t gk = (uint64_t)tau_seen << 32;
           if (gk > st.thr_key) st.thr_key = gk;
@@ -281,7 +286,7 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
               }
               if (__any_sync(kFull, st.cnt == kBufSlots)) {
                 __syncwarp();
-                warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp, scr, stats);
+                warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp, scr, stats, p.flags & 1);
                 thr_f = st.thr_key ? score_of_goodness<true>((uint32_t)(st.thr_key >> 32)) : -INFINITY;
                 thr_pre = COSINE ? prefilter_threshold(thr_f, qinv) : thr_f;
                 // drop hits the tighter threshold already rules out
@@ -299,7 +304,7 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       __syncwarp();
-      warp_compact(st, 1, p.k, buf_warp, lists_warp, tau_warp, scr, stats);   // flush
+      warp_compact(st, 1, p.k, buf_warp, lists_warp, tau_warp, scr, stats, p.flags & 1);   // flush
       // publish: this quarter of the item's lists is final (release after every lane's list writes)
       __threadfence();
       __syncwarp();
@@ -675,6 +680,8 @@ int ia_catalog_topk(ia_catalog* cat, int measure, const void* queries, int64_t q
   p.n_tiles = (int)((cat->c + BN - 1) / BN);
   p.kblocks = (int)((cat->d + tc::BK - 1) / tc::BK);
   p.row_base = cat->row_base;
+  p.flags = 7;
+  if (const char* f = getenv("IA_RETR_FLAGS")) p.flags = atoi(f);
   const int sms = sm_count();
   int ctas = sms;
   if (!use_tc) ctas = sms * 2;

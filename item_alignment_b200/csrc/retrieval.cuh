@@ -47,6 +47,53 @@ __device__ __forceinline__ void warp_load_list(uint64_t (&Lr)[4], const uint64_t
   for (int r = 0; r < 4; ++r) Lr[r] = list[lane + 32 * r];
 }
 
+// Variant A (kept for in-run A/B measurements): binary searches, fewer instructions but dependent chains.
+__device__ __forceinline__ uint64_t warp_merge_loaded_bsearch(const uint64_t (&Lr)[4], uint64_t* list, uint64_t bk, int c, int k,
+                                                      uint64_t* scr) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) scr[lane + 32 * r] = Lr[r];
+  scr[kListCap + lane] = bk;
+  __syncwarp();
+  int rank_b = 0;
+  for (int i = 0; i < c; ++i) rank_b += (scr[kListCap + i] > bk);
+  int lo = 0, hi = kListCap;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {          // answers 0..128: 8 halvings; empty (0) tail entries are < any key
+    const int mid = (lo + hi) >> 1;
+    if (lo < hi) { if (scr[mid] > bk) lo = mid + 1; else hi = mid; }
+  }
+  const int mypos = lo + rank_b;
+  __syncwarp();
+  if (bk != 0) scr[kListCap + rank_b] = bk;   // new keys sorted descending (keys are unique)
+  __syncwarp();
+  uint64_t kth = 0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    if (Lr[r] != 0) {
+      int l2 = 0, h2 = c;
+#pragma unroll
+      for (int it = 0; it < 6; ++it) {       // answers 0..c, c <= 32: 6 halvings
+        const int mid = (l2 + h2) >> 1;
+        if (l2 < h2) { if (scr[kListCap + mid] > Lr[r]) l2 = mid + 1; else h2 = mid; }
+      }
+      const int p = lane + 32 * r + l2;
+      if (p < k) {
+        list[p] = Lr[r];
+        if (p == k - 1) kth = Lr[r];
+      }
+    }
+  }
+  if (bk != 0 && mypos < k) {
+    list[mypos] = bk;
+    if (mypos == k - 1) kth = bk;
+  }
+  __syncwarp();
+  const uint32_t klo = __reduce_or_sync(kFull, (uint32_t)kth);
+  const uint32_t khi = __reduce_or_sync(kFull, (uint32_t)(kth >> 32));
+  return ((uint64_t)khi << 32) | klo;
+}
+
 // MAXC: compile-time bound on c (24 from the append buffers, 32 in the list-merge kernel).
 // Everything is written as short independent instruction streams (broadcast shared-memory loads + compares),
 // not dependent chains: one warp per scheduler runs this, so latency, not issue rate, is what it costs.
@@ -143,7 +190,8 @@ struct CompactResult {
   unsigned merges;
 };
 __device__ __noinline__ CompactResult warp_compact_impl(uint64_t thr_key, int cnt, int min_cnt, int k, uint64_t* buf_warp,
-                                                        uint64_t* lists_warp, uint32_t* tau_global_warp, uint64_t* scr) {
+                                                        uint64_t* lists_warp, uint32_t* tau_global_warp, uint64_t* scr,
+                                                        int variant) {
   TopKThread st{thr_key, cnt};
   TopKStats stats{0u, 0u, 0u, 0u};
   const int lane = threadIdx.x & 31;
@@ -158,7 +206,8 @@ __device__ __noinline__ CompactResult warp_compact_impl(uint64_t thr_key, int cn
     const uint64_t bk = lane < c ? buf_warp[ql * kBufPitch + lane] : 0ull;
     uint64_t Lr[4] = {Lnext[0], Lnext[1], Lnext[2], Lnext[3]};
     if (need) warp_load_list(Lnext, lists_warp + (size_t)(__ffs(need) - 1) * kListCap);
-    const uint64_t kth = warp_merge_loaded<kBufSlots>(Lr, list, bk, c, k, scr);
+    const uint64_t kth = variant ? warp_merge_loaded<kBufSlots>(Lr, list, bk, c, k, scr)
+                                 : warp_merge_loaded_bsearch(Lr, list, bk, c, k, scr);
     stats.compactions++;
     if (lane == ql) {
       st.cnt = 0;
@@ -170,8 +219,8 @@ __device__ __noinline__ CompactResult warp_compact_impl(uint64_t thr_key, int cn
   return CompactResult{st.thr_key, st.cnt, stats.compactions};
 }
 __device__ __forceinline__ void warp_compact(TopKThread& st, int min_cnt, int k, uint64_t* buf_warp, uint64_t* lists_warp,
-                                             uint32_t* tau_global_warp, uint64_t* scr, TopKStats& stats) {
-  const CompactResult r = warp_compact_impl(st.thr_key, st.cnt, min_cnt, k, buf_warp, lists_warp, tau_global_warp, scr);
+                                             uint32_t* tau_global_warp, uint64_t* scr, TopKStats& stats, int variant = 1) {
+  const CompactResult r = warp_compact_impl(st.thr_key, st.cnt, min_cnt, k, buf_warp, lists_warp, tau_global_warp, scr, variant);
   st.thr_key = r.thr_key;
   st.cnt = r.cnt;
   stats.compactions += r.merges;

@@ -13,6 +13,14 @@ dev = torch.device("cuda:0")
 gen = torch.Generator(device=dev).manual_seed(1)
 cat = torch.tanh(torch.randn(c_n, d, device=dev, generator=gen)).to(torch.bfloat16)
 q = torch.tanh(torch.randn(q_n, d, device=dev, generator=gen)).to(torch.bfloat16)
+a = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16); b = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
+for _ in range(3): (a @ b)
+torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10): (a @ b)
+e1.record(); torch.cuda.synchronize()
+print(f"   calib: cuBLAS bf16 8192^3 {10*2*8192**3/e0.elapsed_time(e1)/1e9:.0f} TFLOP/s, flags={os.environ.get('IA_RETR_FLAGS','default')}")
+del a, b
 with ia.CatalogIndex(cat) as index:
     for _ in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
