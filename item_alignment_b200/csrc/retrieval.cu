@@ -582,6 +582,7 @@ struct ia_catalog {
   uint32_t* tau; size_t tau_bytes;      // [tau | done flags]
   float* qinv; size_t qinv_bytes;
   unsigned long long* stats;            // [8]
+  int last_splits, last_tiles_per_split;
 };
 
 static int grow(void** ptr, size_t* have, size_t need) {
@@ -593,19 +594,21 @@ static int grow(void** ptr, size_t* have, size_t need) {
   return IA_OK;
 }
 
-// choose the number of catalog splits: fill the SMs in whole waves, keep splits long enough to amortise warm-up
-static void plan_splits(int n_qt, int n_tiles, int ctas, int min_tiles, int* n_splits, int* tiles_per_split) {
+// Choose the number of catalog splits.  Every (query tile, split) item pays a cold start -- its top-k lists fill
+// and its thresholds tighten from scratch -- worth roughly `penalty` tiles of tensor-core time (it grows with k),
+// so the plan minimises  waves * (tiles_per_split + penalty): fill the SMs in whole waves with as FEW splits as
+// that allows.  (A plan that only maximised wave efficiency picked 40+ splits and spent its time on cold starts.)
+static void plan_splits(int n_qt, int n_tiles, int ctas, int min_tiles, double penalty, int* n_splits, int* tiles_per_split) {
   int best_s = 1;
-  double best_eff = -1.0;
+  double best_cost = 1e300;
   const int max_s = n_tiles / min_tiles > 1 ? n_tiles / min_tiles : 1;
-  for (int s = 1; s <= max_s && s <= 256; ++s) {
+  for (int s = 1; s <= max_s && s <= 32; ++s) {      // <= 32: the finished-split bound tracks 32 splits
     const int tps = (n_tiles + s - 1) / s;
     const int real_s = (n_tiles + tps - 1) / tps;
     const int64_t items = (int64_t)n_qt * real_s;
     const int64_t waves = (items + ctas - 1) / ctas;
-    // time ~ waves * tps ; ideal ~ n_qt * n_tiles / ctas
-    const double eff = ((double)n_qt * n_tiles / ctas) / ((double)waves * tps);
-    if (eff > best_eff + 1e-9) { best_eff = eff; best_s = real_s; }
+    const double cost = (double)waves * ((double)tps + penalty);
+    if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; best_s = real_s; }
   }
   *n_splits = best_s;
   *tiles_per_split = (n_tiles + best_s - 1) / best_s;
@@ -680,12 +683,14 @@ int ia_catalog_topk(ia_catalog* cat, int measure, const void* queries, int64_t q
   p.n_tiles = (int)((cat->c + BN - 1) / BN);
   p.kblocks = (int)((cat->d + tc::BK - 1) / tc::BK);
   p.row_base = cat->row_base;
-  p.flags = 7;
+  p.flags = 6;
   if (const char* f = getenv("IA_RETR_FLAGS")) p.flags = atoi(f);
   const int sms = sm_count();
   int ctas = sms;
   if (!use_tc) ctas = sms * 2;
-  plan_splits(p.n_qt, p.n_tiles, ctas, use_tc ? 8 : 4, &p.n_splits, &p.tiles_per_split);
+  double penalty = (use_tc ? 0.6 : 0.15) * k;
+  if (const char* f = getenv("IA_RETR_PENALTY")) penalty = atof(f) * k;
+  plan_splits(p.n_qt, p.n_tiles, ctas, use_tc ? 8 : 4, penalty, &p.n_splits, &p.tiles_per_split);
   const int64_t n_items = (int64_t)p.n_qt * p.n_splits;
 
   int rc;
@@ -694,6 +699,7 @@ int ia_catalog_topk(ia_catalog* cat, int measure, const void* queries, int64_t q
   if ((rc = grow((void**)&cat->tau, &cat->tau_bytes, sizeof(uint32_t) * (tau_n + done_n))) != IA_OK) return rc;
   IA_CUDA_CHECK(cudaMemsetAsync(cat->tau, 0, sizeof(uint32_t) * (tau_n + done_n), s));
   IA_CUDA_CHECK(cudaMemsetAsync(cat->stats, 0, sizeof(unsigned long long) * 8, s));
+  cat->last_splits = p.n_splits; cat->last_tiles_per_split = p.tiles_per_split;
   p.lists = cat->lists; p.tau_global = cat->tau; p.done = cat->tau + tau_n; p.cinv = cat->cinv; p.stats = cat->stats;
   if (measure == IA_COSINE) {
     if ((rc = grow((void**)&cat->qinv, &cat->qinv_bytes, sizeof(float) * (size_t)q)) != IA_OK) return rc;
@@ -744,6 +750,8 @@ int ia_catalog_topk(ia_catalog* cat, int measure, const void* queries, int64_t q
 int ia_catalog_last_stats(ia_catalog* cat, uint64_t* out8) {
   if (cat == nullptr || out8 == nullptr) { set_error("bad arguments"); return IA_ERR_INVALID; }
   IA_CUDA_CHECK(cudaMemcpy(out8, cat->stats, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost));   // synchronising
+  out8[4] = (uint64_t)cat->last_splits;
+  out8[5] = (uint64_t)cat->last_tiles_per_split;
   return IA_OK;
 }
 

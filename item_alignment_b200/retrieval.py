@@ -85,7 +85,8 @@ class CatalogIndex:
         """Telemetry of the last topk call (synchronises): appended keys, merges, rare groups, rare blocks."""
         out = (ctypes.c_uint64 * 8)()
         check(lib().ia_catalog_last_stats(self._h, out))
-        return dict(appends=out[0], compactions=out[1], rare_groups=out[2], rare_blocks=out[3])
+        return dict(appends=out[0], compactions=out[1], rare_groups=out[2], rare_blocks=out[3], splits=out[4],
+                    tiles_per_split=out[5])
 
 
 def unpack_keys(keys, measure):

@@ -9,6 +9,7 @@ c_n = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
 d = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
 measure = sys.argv[4] if len(sys.argv) > 4 else "cosine"
 k = int(sys.argv[5]) if len(sys.argv) > 5 else 100
+reps = int(sys.argv[6]) if len(sys.argv) > 6 else 8
 dev = torch.device("cuda:0")
 gen = torch.Generator(device=dev).manual_seed(1)
 cat = torch.tanh(torch.randn(c_n, d, device=dev, generator=gen)).to(torch.bfloat16)
@@ -22,13 +23,17 @@ e1.record(); torch.cuda.synchronize()
 print(f"   calib: cuBLAS bf16 8192^3 {10*2*8192**3/e0.elapsed_time(e1)/1e9:.0f} TFLOP/s, flags={os.environ.get('IA_RETR_FLAGS','default')}")
 del a, b
 with ia.CatalogIndex(cat) as index:
-    for _ in range(3):
+    times = []
+    for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         keys = index.topk_keys(q, k, measure)
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        st = index.last_stats()
-        print(f"   stats per query: appends {st['appends']/q_n:.0f} compactions {st['compactions']/q_n:.1f}; rare groups {st['rare_groups']} blocks {st['rare_blocks']}")
+        times.append(e0.elapsed_time(e1))
+    st = index.last_stats()
+    import statistics
+    ms = statistics.median(times[1:])
+    print(f"   stats per query: appends {st['appends']/q_n:.0f} compactions {st['compactions']/q_n:.1f}; rare groups {st['rare_groups']} iters {st['rare_blocks']}; splits {st['splits']} x {st['tiles_per_split']} tiles; min {min(times):.2f} ms")
+    if True:
         print(f"{measure} k={k} Q={q_n} C={c_n} D={d}: {ms:.2f} ms, {2.0*q_n*c_n*d/ms/1e9:.1f} TFLOP/s, {q_n/ms*1e3:.0f} q/s")
