@@ -134,8 +134,11 @@ void ia_catalog_destroy(ia_catalog* cat);
 int ia_catalog_topk(ia_catalog* cat, int measure, const void* queries, int64_t q, int64_t ldq,
                     int k, uint64_t* keys_out, ia_stream_t stream);
 /* Telemetry of the last ia_catalog_topk on this handle (synchronises the device): out8[0] keys appended to the
- * per-query buffers, [1] buffer->list merges, [2] 32-column groups and [3] 8-column blocks that left the fast path. */
+ * per-query buffers, [1] buffer->list merges, [2] 32-column groups that left the fast path, [3] rare-path
+ * iterations, and epilogue-warp cycle sums: [4] waiting for accumulators, [5] in merges, [6] total, [7] rare path. */
 int ia_catalog_last_stats(ia_catalog* cat, uint64_t* out8);
+/* The work decomposition ia_catalog_topk chose last: catalog splits and 256-row tiles per split. */
+int ia_catalog_last_plan(ia_catalog* cat, int* splits, int* tiles_per_split);
 /* merge `parts` sorted key lists [parts, q, k] -> [q, k] (after the all-gather of shard results) */
 int ia_topk_merge(const uint64_t* keys_in, int parts, int64_t q, int k, uint64_t* keys_out,
                   ia_stream_t stream);

@@ -203,6 +203,8 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     uint64_t* buf_warp = buf + (size_t)(e * 32) * kBufPitch;
     uint64_t* scr = scr_all + (size_t)(warp - 2) * kScrWords;
     TopKStats stats{0u, 0u, 0u, 0u};
+    long long cyc_wait = 0, cyc_compact = 0, cyc_rare = 0;
+    const long long cyc_begin = clock64();
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -226,9 +228,11 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         // what other CTAs have published for this query: issue the (L2-latency) load now, consume it after the waits
         uint32_t tau_seen = 0;
         if (p.flags & 2) tau_seen = *reinterpret_cast<volatile uint32_t*>(tau_warp + lane);
+        const long long w0 = clock64();
         if (COSINE) mbar_wait(&cfull_bar[acc], acc_phase);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
+        cyc_wait += clock64() - w0;
         if (!(p.flags & 2)) tau_seen = *reinterpret_cast<volatile uint32_t*>(tau_warp + lane);
         {
           const uint64_t gk = (uint64_t)tau_seen << 32;
@@ -266,6 +270,8 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           if (!q_ok) mask = 0;
           if (__any_sync(kFull, mask != 0)) {
             stats.rare_groups++;
+            const long long r0 = clock64();
+            long long c_in = 0;
             // rare path: every lane walks its own hits (usually one), all lanes in parallel
             while (__any_sync(kFull, mask != 0)) {
               stats.rare_blocks++;
@@ -286,7 +292,9 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
               }
               if (__any_sync(kFull, st.cnt == kBufSlots)) {
                 __syncwarp();
+                const long long c0 = clock64();
                 warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp, scr, stats, p.flags & 1);
+                c_in += clock64() - c0;
                 thr_f = st.thr_key ? score_of_goodness<true>((uint32_t)(st.thr_key >> 32)) : -INFINITY;
                 thr_pre = COSINE ? prefilter_threshold(thr_f, qinv) : thr_f;
                 // drop hits the tighter threshold already rules out
@@ -296,6 +304,8 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 mask &= m2;
               }
             }
+            cyc_compact += c_in;
+            cyc_rare += clock64() - r0 - c_in;
           }
         }
         tc_fence_before();
@@ -320,6 +330,10 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         atomicAdd(p.stats + 1, (unsigned long long)stats.compactions);
         atomicAdd(p.stats + 2, (unsigned long long)stats.rare_groups);
         atomicAdd(p.stats + 3, (unsigned long long)stats.rare_blocks);
+        atomicAdd(p.stats + 4, (unsigned long long)cyc_wait);
+        atomicAdd(p.stats + 5, (unsigned long long)cyc_compact);
+        atomicAdd(p.stats + 6, (unsigned long long)(clock64() - cyc_begin));
+        atomicAdd(p.stats + 7, (unsigned long long)cyc_rare);
       }
     }
   }
@@ -747,11 +761,16 @@ int ia_catalog_topk(ia_catalog* cat, int measure, const void* queries, int64_t q
   return IA_OK;
 }
 
+int ia_catalog_last_plan(ia_catalog* cat, int* splits, int* tiles_per_split) {
+  if (cat == nullptr) { set_error("bad arguments"); return IA_ERR_INVALID; }
+  if (splits) *splits = cat->last_splits;
+  if (tiles_per_split) *tiles_per_split = cat->last_tiles_per_split;
+  return IA_OK;
+}
+
 int ia_catalog_last_stats(ia_catalog* cat, uint64_t* out8) {
   if (cat == nullptr || out8 == nullptr) { set_error("bad arguments"); return IA_ERR_INVALID; }
   IA_CUDA_CHECK(cudaMemcpy(out8, cat->stats, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost));   // synchronising
-  out8[4] = (uint64_t)cat->last_splits;
-  out8[5] = (uint64_t)cat->last_tiles_per_split;
   return IA_OK;
 }
 

@@ -85,8 +85,10 @@ class CatalogIndex:
         """Telemetry of the last topk call (synchronises): appended keys, merges, rare groups, rare blocks."""
         out = (ctypes.c_uint64 * 8)()
         check(lib().ia_catalog_last_stats(self._h, out))
-        return dict(appends=out[0], compactions=out[1], rare_groups=out[2], rare_blocks=out[3], splits=out[4],
-                    tiles_per_split=out[5])
+        sp, tp = ctypes.c_int(0), ctypes.c_int(0)
+        check(lib().ia_catalog_last_plan(self._h, ctypes.byref(sp), ctypes.byref(tp)))
+        return dict(appends=out[0], compactions=out[1], rare_groups=out[2], rare_blocks=out[3], cyc_wait=out[4],
+                    cyc_compact=out[5], cyc_total=out[6], cyc_rare=out[7], splits=sp.value, tiles_per_split=tp.value)
 
 
 def unpack_keys(keys, measure):

@@ -34,6 +34,6 @@ with ia.CatalogIndex(cat) as index:
     st = index.last_stats()
     import statistics
     ms = statistics.median(times[1:])
-    print(f"   stats per query: appends {st['appends']/q_n:.0f} compactions {st['compactions']/q_n:.1f}; rare groups {st['rare_groups']} iters {st['rare_blocks']}; splits {st['splits']} x {st['tiles_per_split']} tiles; min {min(times):.2f} ms")
+    print(f"   stats per query: appends {st['appends']/q_n:.0f} compactions {st['compactions']/q_n:.1f}; rare groups {st['rare_groups']} iters {st['rare_blocks']}; splits {st['splits']} x {st['tiles_per_split']} tiles; min {min(times):.2f} ms; epilogue cycles: wait {100*st['cyc_wait']/max(1,st['cyc_total']):.0f}% merge {100*st['cyc_compact']/max(1,st['cyc_total']):.0f}% rare {100*st['cyc_rare']/max(1,st['cyc_total']):.0f}% total/warp {st['cyc_total']/592/1e6:.1f}M")
     if True:
         print(f"{measure} k={k} Q={q_n} C={c_n} D={d}: {ms:.2f} ms, {2.0*q_n*c_n*d/ms/1e9:.1f} TFLOP/s, {q_n/ms*1e3:.0f} q/s")
