@@ -310,8 +310,15 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // accumulator released: the MMA warp may overwrite it
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        // list maintenance OUTSIDE the accumulator's critical section: half-full buffers are merged now, while the
+        // tensor core works on the next tiles, so that buffers rarely fill up (and force a merge) mid-tile
+        if (__any_sync(kFull, st.cnt >= kBufSlots / 2)) {
+          const long long c0 = clock64();
+          warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp, scr, stats, p.flags & 1);
+          cyc_compact += clock64() - c0;
+        }
       }
       __syncwarp();
       warp_compact(st, 1, p.k, buf_warp, lists_warp, tau_warp, scr, stats, p.flags & 1);   // flush
@@ -702,7 +709,7 @@ int ia_catalog_topk(ia_catalog* cat, int measure, const void* queries, int64_t q
   const int sms = sm_count();
   int ctas = sms;
   if (!use_tc) ctas = sms * 2;
-  double penalty = (use_tc ? 0.6 : 0.15) * k;
+  double penalty = (use_tc ? 0.3 : 0.15) * k;
   if (const char* f = getenv("IA_RETR_PENALTY")) penalty = atof(f) * k;
   plan_splits(p.n_qt, p.n_tiles, ctas, use_tc ? 8 : 4, penalty, &p.n_splits, &p.tiles_per_split);
   const int64_t n_items = (int64_t)p.n_qt * p.n_splits;

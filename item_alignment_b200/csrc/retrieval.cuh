@@ -47,16 +47,20 @@ __device__ __forceinline__ void warp_load_list(uint64_t (&Lr)[4], const uint64_t
   for (int r = 0; r < 4; ++r) Lr[r] = list[lane + 32 * r];
 }
 
-// Variant A (kept for in-run A/B measurements): binary searches, fewer instructions but dependent chains.
+// Variant A: binary searches.  The searches are written step-major (the four list entries of a lane advance one
+// halving at a time together) and the new-key rank loop is fully unrolled, so the shared-memory latencies of
+// independent chains overlap instead of adding up.
+template <int MAXC>
 __device__ __forceinline__ uint64_t warp_merge_loaded_bsearch(const uint64_t (&Lr)[4], uint64_t* list, uint64_t bk, int c, int k,
-                                                      uint64_t* scr) {
+                                                              uint64_t* scr) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int r = 0; r < 4; ++r) scr[lane + 32 * r] = Lr[r];
   scr[kListCap + lane] = bk;
   __syncwarp();
   int rank_b = 0;
-  for (int i = 0; i < c; ++i) rank_b += (scr[kListCap + i] > bk);
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) rank_b += (i < c && scr[kListCap + i] > bk) ? 1 : 0;
   int lo = 0, hi = kListCap;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {          // answers 0..128: 8 halvings; empty (0) tail entries are < any key
@@ -67,17 +71,21 @@ __device__ __forceinline__ uint64_t warp_merge_loaded_bsearch(const uint64_t (&L
   __syncwarp();
   if (bk != 0) scr[kListCap + rank_b] = bk;   // new keys sorted descending (keys are unique)
   __syncwarp();
+  int l2[4] = {0, 0, 0, 0}, h2[4] = {c, c, c, c};
+#pragma unroll
+  for (int it = 0; it < 6; ++it) {           // answers 0..c, c <= 32: 6 halvings, four searches in lockstep
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int mid = (l2[r] + h2[r]) >> 1;
+      const uint64_t probe = scr[kListCap + (mid < 31 ? mid : 31)];
+      if (l2[r] < h2[r]) { if (probe > Lr[r]) l2[r] = mid + 1; else h2[r] = mid; }
+    }
+  }
   uint64_t kth = 0;
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     if (Lr[r] != 0) {
-      int l2 = 0, h2 = c;
-#pragma unroll
-      for (int it = 0; it < 6; ++it) {       // answers 0..c, c <= 32: 6 halvings
-        const int mid = (l2 + h2) >> 1;
-        if (l2 < h2) { if (scr[kListCap + mid] > Lr[r]) l2 = mid + 1; else h2 = mid; }
-      }
-      const int p = lane + 32 * r + l2;
+      const int p = lane + 32 * r + l2[r];
       if (p < k) {
         list[p] = Lr[r];
         if (p == k - 1) kth = Lr[r];
@@ -162,7 +170,7 @@ __device__ __forceinline__ uint64_t warp_merge_loaded(const uint64_t (&Lr)[4], u
 __device__ __forceinline__ uint64_t warp_merge_keys(uint64_t* list, uint64_t bk, int c, int k, uint64_t* scr) {
   uint64_t Lr[4];
   warp_load_list(Lr, list);
-  return warp_merge_loaded<32>(Lr, list, bk, c, k, scr);
+  return warp_merge_loaded_bsearch<32>(Lr, list, bk, c, k, scr);
 }
 
 // Streaming top-k state of ONE query, owned by one thread; 32 queries (one warp) are compacted together.
@@ -207,7 +215,7 @@ __device__ __noinline__ CompactResult warp_compact_impl(uint64_t thr_key, int cn
     uint64_t Lr[4] = {Lnext[0], Lnext[1], Lnext[2], Lnext[3]};
     if (need) warp_load_list(Lnext, lists_warp + (size_t)(__ffs(need) - 1) * kListCap);
     const uint64_t kth = variant ? warp_merge_loaded<kBufSlots>(Lr, list, bk, c, k, scr)
-                                 : warp_merge_loaded_bsearch(Lr, list, bk, c, k, scr);
+                                 : warp_merge_loaded_bsearch<kBufSlots>(Lr, list, bk, c, k, scr);
     stats.compactions++;
     if (lane == ql) {
       st.cnt = 0;
