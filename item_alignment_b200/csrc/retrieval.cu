@@ -39,7 +39,7 @@ struct RetrParams {
   unsigned long long* stats;  // [8] appends, compactions, rare groups, rare blocks (telemetry)
   uint32_t row_base;    // global row id of catalog row 0 (shard offset)
   int flags;            // tuning switches for in-run A/B measurements (env IA_RETR_FLAGS): bit0 merge variant,
-                        // bit1 early tau load, bit2 finished-split bound
+                        // bit1 early tau load, bit2 finished-split bound, bit3 paced merges (<= 2 lanes per tile after release)
 };
 
 // A valid lower bound on the final k-th best key of a query from the FINISHED splits of its query tile:
@@ -293,7 +293,7 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
               if (__any_sync(kFull, st.cnt == kBufSlots)) {
                 __syncwarp();
                 const long long c0 = clock64();
-                warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp, scr, stats, p.flags & 1);
+                warp_compact(st, (p.flags & 8) ? kBufSlots : kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp, scr, stats, p.flags & 1);
                 c_in += clock64() - c0;
                 thr_f = st.thr_key ? score_of_goodness<true>((uint32_t)(st.thr_key >> 32)) : -INFINITY;
                 thr_pre = COSINE ? prefilter_threshold(thr_f, qinv) : thr_f;
@@ -316,7 +316,7 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         // tensor core works on the next tiles, so that buffers rarely fill up (and force a merge) mid-tile
         if (__any_sync(kFull, st.cnt >= kBufSlots / 2)) {
           const long long c0 = clock64();
-          warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp, scr, stats, p.flags & 1);
+          warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp, scr, stats, p.flags & 1, (p.flags & 8) ? 2 : 32);
           cyc_compact += clock64() - c0;
         }
       }
@@ -704,7 +704,7 @@ int ia_catalog_topk(ia_catalog* cat, int measure, const void* queries, int64_t q
   p.n_tiles = (int)((cat->c + BN - 1) / BN);
   p.kblocks = (int)((cat->d + tc::BK - 1) / tc::BK);
   p.row_base = cat->row_base;
-  p.flags = 6;
+  p.flags = 14;
   if (const char* f = getenv("IA_RETR_FLAGS")) p.flags = atoi(f);
   const int sms = sm_count();
   int ctas = sms;

@@ -199,36 +199,45 @@ struct CompactResult {
 };
 __device__ __noinline__ CompactResult warp_compact_impl(uint64_t thr_key, int cnt, int min_cnt, int k, uint64_t* buf_warp,
                                                         uint64_t* lists_warp, uint32_t* tau_global_warp, uint64_t* scr,
-                                                        int variant) {
+                                                        int variant, int max_lanes) {
   TopKThread st{thr_key, cnt};
-  TopKStats stats{0u, 0u, 0u, 0u};
+  unsigned merges = 0;
   const int lane = threadIdx.x & 31;
-  unsigned need = __ballot_sync(kFull, st.cnt >= min_cnt && st.cnt > 0);
-  uint64_t Lnext[4] = {0, 0, 0, 0};
-  if (need) warp_load_list(Lnext, lists_warp + (size_t)(__ffs(need) - 1) * kListCap);
-  while (need) {
-    const int ql = __ffs(need) - 1;
-    need &= need - 1;
-    const int c = __shfl_sync(kFull, st.cnt, ql);
+  // fullest buffers first, at most max_lanes of them: bounded work per call keeps the epilogue's pace even
+  int mx = __reduce_max_sync(kFull, st.cnt);
+  if (mx < min_cnt || mx == 0) return CompactResult{st.thr_key, st.cnt, 0u};
+  int ql = __ffs(__ballot_sync(kFull, st.cnt == mx)) - 1;
+  uint64_t Lnext[4];
+  warp_load_list(Lnext, lists_warp + (size_t)ql * kListCap);
+  while (true) {
+    const int c = mx;
     uint64_t* list = lists_warp + (size_t)ql * kListCap;
     const uint64_t bk = lane < c ? buf_warp[ql * kBufPitch + lane] : 0ull;
     uint64_t Lr[4] = {Lnext[0], Lnext[1], Lnext[2], Lnext[3]};
-    if (need) warp_load_list(Lnext, lists_warp + (size_t)(__ffs(need) - 1) * kListCap);
+    if (lane == ql) st.cnt = 0;
+    ++merges;
+    // pick (and prefetch) the next lane before merging this one
+    mx = __reduce_max_sync(kFull, st.cnt);
+    const bool more = (int)merges < max_lanes && mx >= min_cnt && mx > 0;
+    const int qn = more ? __ffs(__ballot_sync(kFull, st.cnt == mx)) - 1 : 0;
+    if (more) warp_load_list(Lnext, lists_warp + (size_t)qn * kListCap);
     const uint64_t kth = variant ? warp_merge_loaded<kBufSlots>(Lr, list, bk, c, k, scr)
                                  : warp_merge_loaded_bsearch<kBufSlots>(Lr, list, bk, c, k, scr);
-    stats.compactions++;
     if (lane == ql) {
-      st.cnt = 0;
       if (kth > st.thr_key) st.thr_key = kth;
       if (tau_global_warp != nullptr && kth != 0) atomicMax(tau_global_warp + ql, (uint32_t)(kth >> 32));
     }
+    if (!more) break;
+    ql = qn;
   }
   __syncwarp();
-  return CompactResult{st.thr_key, st.cnt, stats.compactions};
+  return CompactResult{st.thr_key, st.cnt, merges};
 }
 __device__ __forceinline__ void warp_compact(TopKThread& st, int min_cnt, int k, uint64_t* buf_warp, uint64_t* lists_warp,
-                                             uint32_t* tau_global_warp, uint64_t* scr, TopKStats& stats, int variant = 1) {
-  const CompactResult r = warp_compact_impl(st.thr_key, st.cnt, min_cnt, k, buf_warp, lists_warp, tau_global_warp, scr, variant);
+                                             uint32_t* tau_global_warp, uint64_t* scr, TopKStats& stats, int variant = 0,
+                                             int max_lanes = 32) {
+  const CompactResult r = warp_compact_impl(st.thr_key, st.cnt, min_cnt, k, buf_warp, lists_warp, tau_global_warp, scr, variant,
+                                            max_lanes);
   st.thr_key = r.thr_key;
   st.cnt = r.cnt;
   stats.compactions += r.merges;
