@@ -104,7 +104,7 @@ def cpu_reference_step(torch, x, y, labels):
     return torch_port.pair_score_loss_fwd_bwd("inner_product", "bce", x, y, labels)
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, emit):
     import torch
     if rank != 0:
         return
@@ -129,7 +129,7 @@ def run_reference(args, rank):
     dt = time.perf_counter() - t
     val = rows * args.steps / dt
     sample = f"{rows} of {N_PAIRS} pairs x {DIM}-d per step, bf16 inputs upcast to fp32 as the reference's autocast does, {args.steps} steps"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": "pairs/s (fused score+loss fwd/bwd)", "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -196,6 +196,13 @@ def bench_retrieval(torch, dist, ia, device, rank, world, pk):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything libraries print (e.g. "NCCL version ...") goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -210,7 +217,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, emit)
         return
 
     import torch
@@ -329,7 +336,7 @@ def main():
                          "frac_of_nominal_8000": gbs / 8000.0, "per_gpu": True},
             "cpu_baseline": cpu, "retrieval": retrieval,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -101,7 +101,7 @@ constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTE
 constexpr int THREADS = 192;
 constexpr int BUF_BYTES = BM * kBufPitch * 8;
 constexpr int CINV_BYTES = 2 * BN * 4;
-constexpr int SCR_BYTES = 4 * kScrWords * 8;
+constexpr int SCR_BYTES = 0;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BUF_BYTES + CINV_BYTES + SCR_BYTES + 256 + 1024;  // + barriers + align slack
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 }  // namespace tc
@@ -116,7 +116,6 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* buf = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   float* cinv_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BUF_BYTES);
-  uint64_t* scr_all = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + BUF_BYTES + CINV_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + BUF_BYTES + CINV_BYTES + SCR_BYTES);
   uint64_t* full_bar = bars;                // [STAGES] TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;      // [STAGES] MMA -> TMA
@@ -201,7 +200,6 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const int e = warp & 3;                 // TMEM lane quarter this warp may access
     const int row_local = e * 32 + lane;    // query row inside the tile == TMEM lane
     uint64_t* buf_warp = buf + (size_t)(e * 32) * kBufPitch;
-    uint64_t* scr = scr_all + (size_t)(warp - 2) * kScrWords;
     TopKStats stats{0u, 0u, 0u, 0u};
     long long cyc_wait = 0, cyc_compact = 0, cyc_rare = 0;
     const long long cyc_begin = clock64();
@@ -293,7 +291,7 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
               if (__any_sync(kFull, st.cnt == kBufSlots)) {
                 __syncwarp();
                 const long long c0 = clock64();
-                warp_compact(st, (p.flags & 8) ? kBufSlots : kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp, scr, stats, p.flags & 1);
+                warp_compact(st, (p.flags & 8) ? kBufSlots : kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp, stats);
                 c_in += clock64() - c0;
                 thr_f = st.thr_key ? score_of_goodness<true>((uint32_t)(st.thr_key >> 32)) : -INFINITY;
                 thr_pre = COSINE ? prefilter_threshold(thr_f, qinv) : thr_f;
@@ -316,12 +314,12 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         // tensor core works on the next tiles, so that buffers rarely fill up (and force a merge) mid-tile
         if (__any_sync(kFull, st.cnt >= kBufSlots / 2)) {
           const long long c0 = clock64();
-          warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp, scr, stats, p.flags & 1, (p.flags & 8) ? 2 : 32);
+          warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp, stats, (p.flags & 8) ? 2 : 32);
           cyc_compact += clock64() - c0;
         }
       }
       __syncwarp();
-      warp_compact(st, 1, p.k, buf_warp, lists_warp, tau_warp, scr, stats, p.flags & 1);   // flush
+      warp_compact(st, 1, p.k, buf_warp, lists_warp, tau_warp, stats);   // flush
       // publish: this quarter of the item's lists is final (release after every lane's list writes)
       __threadfence();
       __syncwarp();
@@ -359,7 +357,7 @@ namespace simt {
 constexpr int BM = 64, BN = 128, BK = 32, THREADS = 256;
 constexpr int QS = BK * (BM + 1), CS = BK * (BN + 1), SS = BM * (BN + 1);
 constexpr int STAGE_FLOATS = (QS + CS) > SS ? (QS + CS) : SS;
-constexpr int SMEM_BYTES = STAGE_FLOATS * 4 + BM * kBufPitch * 8 + 2 * kScrWords * 8;
+constexpr int SMEM_BYTES = STAGE_FLOATS * 4 + BM * kBufPitch * 8;
 }  // namespace simt
 
 template <typename T, int MEASURE>
@@ -373,7 +371,6 @@ retrieve_simt_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__
   float* Cs = Qs + QS;                              // [BK][BN+1]
   float* Ss = reinterpret_cast<float*>(smem_raw);   // [BM][BN+1] (aliases the staging tiles)
   uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw + STAGE_FLOATS * 4);
-  uint64_t* scr = buf + BM * kBufPitch + (size_t)((threadIdx.x >> 5) & 1) * kScrWords;
   TopKStats stats{0u, 0u, 0u, 0u};
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ty = tid >> 4, tx = tid & 15;
@@ -471,7 +468,7 @@ retrieve_simt_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__
           }
           if (__any_sync(kFull, st.cnt == kBufSlots)) {
             __syncwarp();
-            warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp, scr, stats);
+            warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp, stats);
             thr_f = st.thr_key ? score_of_goodness<DESC>((uint32_t)(st.thr_key >> 32)) : (DESC ? -INFINITY : INFINITY);
           }
         }
@@ -479,7 +476,7 @@ retrieve_simt_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__
     }
     if (warp < 2) {
       __syncwarp();
-      warp_compact(st, 1, p.k, buf_warp, lists_warp, tau_warp, scr, stats);
+      warp_compact(st, 1, p.k, buf_warp, lists_warp, tau_warp, stats);
       __threadfence();
       __syncwarp();
       if (lane == 0) {
@@ -497,31 +494,26 @@ retrieve_simt_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__
 __global__ void __launch_bounds__(256) merge_lists_kernel(const uint64_t* __restrict__ src, int parts, int64_t q_rows,
                                                           int n_qt, int tile_rows, int src_len, int k,
                                                           uint64_t* __restrict__ out) {
-  __shared__ uint64_t work[8][kListCap];
-  __shared__ uint64_t scratch[8][kScrWords];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint64_t* list = work[warp];
-  uint64_t* scr = scratch[warp];
   for (int64_t q = (int64_t)blockIdx.x * 8 + warp; q < q_rows; q += (int64_t)gridDim.x * 8) {
-    for (int i = lane; i < kListCap; i += 32) list[i] = 0ull;
-    __syncwarp();
-    uint64_t kth = 0;
+    uint64_t A[4] = {0, 0, 0, 0};
     for (int part = 0; part < parts; ++part) {
       const uint64_t* s = tile_rows > 0
           ? src + (((size_t)part * n_qt + (size_t)(q / tile_rows)) * tile_rows + (size_t)(q % tile_rows)) * kListCap
           : src + ((size_t)part * q_rows + (size_t)q) * src_len;
-      for (int b = 0; b < src_len; b += 32) {
-        const uint64_t bk = (b + lane < src_len) ? s[b + lane] : 0ull;
-        // sorted descending: once the batch's best key cannot enter the list, the rest of this part cannot either
-        const uint64_t head = __shfl_sync(kFull, bk, 0);
-        if (head == 0 || (kth != 0 && head < kth)) break;
-        const int c = __popc(__ballot_sync(kFull, bk != 0));
-        kth = warp_merge_keys(list, bk, c, k, scr);
+      uint64_t B[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) B[r] = (lane + 32 * r < src_len) ? __ldg(s + lane + 32 * r) : 0ull;
+      if (part == 0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) A[r] = B[r];
+      } else {
+        warp_merge_lists(A, B);      // one bitonic merge per part: ~200 shuffle/compare instructions
       }
     }
-    __syncwarp();
-    for (int i = lane; i < k; i += 32) out[(size_t)q * k + i] = list[i];
-    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (lane + 32 * r < k) out[(size_t)q * k + lane + 32 * r] = A[r];
   }
 }
 

@@ -32,145 +32,76 @@ constexpr int kListCap = 128;   // IA_MAX_K: list entries per query (4 per lane)
 constexpr int kBufSlots = 24;   // append-buffer slots per query
 constexpr int kBufPitch = kBufSlots + 1;  // u64 words per query in shared memory (padded)
 
-constexpr int kScrWords = kListCap + 32;   // per-warp shared scratch of the merge: staged list + new keys
+// ---------------------------------------------------------------------------------- warp-level list merges
+// A per-query list is 128 keys sorted descending, held by a warp 4 per lane in STRIPED order (register r of
+// lane l is position l + 32*r; empty = 0 sinks to the end).  Merging is done with bitonic networks on
+// registers + shuffles: no shared memory, no data-dependent addressing, 4 independent chains per stage.
+__device__ __forceinline__ uint64_t u64max(uint64_t a, uint64_t b) { return a > b ? a : b; }
+__device__ __forceinline__ uint64_t u64min(uint64_t a, uint64_t b) { return a < b ? a : b; }
 
-// Warp-cooperative merge of up to 32 new keys (one per lane, 0 = none; lanes 0..c-1 hold them) into a sorted
-// (descending) list of <= 128 keys in global memory.  Rank based, every lane works in parallel:
-//   new key : position = (#list entries larger, binary search in the staged list)
-//                      + (#new keys larger, c broadcast compares)
-//   list entry at p : moves down by #new keys larger (binary search in the sorted new keys)
-// Writes the first k positions back to `list`, returns the key at position k-1 (0 if the merged list is
-// shorter than k) to all lanes.  scr: kScrWords u64 of shared memory owned by this warp.
+// Sort a bitonic 128-sequence (striped over the warp) into descending order: strides 64, 32 live inside a
+// thread, strides 16..1 are shuffles.
+__device__ __forceinline__ void warp_bitonic_finish_desc(uint64_t (&A)[4]) {
+  const int lane = threadIdx.x & 31;
+  uint64_t hi, lo;
+  hi = u64max(A[0], A[2]); lo = u64min(A[0], A[2]); A[0] = hi; A[2] = lo;      // stride 64
+  hi = u64max(A[1], A[3]); lo = u64min(A[1], A[3]); A[1] = hi; A[3] = lo;
+  hi = u64max(A[0], A[1]); lo = u64min(A[0], A[1]); A[0] = hi; A[1] = lo;      // stride 32
+  hi = u64max(A[2], A[3]); lo = u64min(A[2], A[3]); A[2] = hi; A[3] = lo;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    const bool lower = (lane & s) == 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint64_t o = __shfl_xor_sync(kFull, A[r], s);
+      A[r] = lower ? u64max(A[r], o) : u64min(A[r], o);
+    }
+  }
+}
+
+// A <- top-128 of (A  U  B), both sorted descending, striped.  C[i] = max(A[i], B[127-i]) is bitonic and holds
+// the 128 largest of the union; then finish the sort.
+__device__ __forceinline__ void warp_merge_lists(uint64_t (&A)[4], const uint64_t (&B)[4]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) A[r] = u64max(A[r], __shfl_sync(kFull, B[3 - r], 31 - lane));
+  warp_bitonic_finish_desc(A);
+}
+
+// A <- top-128 of (A  U  {one new key per lane, unsorted, 0 = none}).
+__device__ __forceinline__ void warp_list_insert(uint64_t (&A)[4], uint64_t nk) {
+  const int lane = threadIdx.x & 31;
+  // bitonic sort of the 32 new keys, descending by lane
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint64_t o = __shfl_xor_sync(kFull, nk, j);
+      const bool desc = (k == 32) || ((lane & k) == 0);
+      const bool keep_max = (((lane & j) == 0) == desc);
+      nk = keep_max ? u64max(nk, o) : u64min(nk, o);
+    }
+  }
+  // new keys occupy positions 0..31 of a (zero padded) sorted list B: B[127-p] is non-empty only for p >= 96
+  A[3] = u64max(A[3], __shfl_sync(kFull, nk, 31 - lane));
+  warp_bitonic_finish_desc(A);
+}
+
 __device__ __forceinline__ void warp_load_list(uint64_t (&Lr)[4], const uint64_t* list) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int r = 0; r < 4; ++r) Lr[r] = list[lane + 32 * r];
 }
-
-// Variant A: binary searches.  The searches are written step-major (the four list entries of a lane advance one
-// halving at a time together) and the new-key rank loop is fully unrolled, so the shared-memory latencies of
-// independent chains overlap instead of adding up.
-template <int MAXC>
-__device__ __forceinline__ uint64_t warp_merge_loaded_bsearch(const uint64_t (&Lr)[4], uint64_t* list, uint64_t bk, int c, int k,
-                                                              uint64_t* scr) {
+__device__ __forceinline__ void warp_store_list(uint64_t* list, const uint64_t (&Lr)[4]) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) scr[lane + 32 * r] = Lr[r];
-  scr[kListCap + lane] = bk;
-  __syncwarp();
-  int rank_b = 0;
-#pragma unroll
-  for (int i = 0; i < MAXC; ++i) rank_b += (i < c && scr[kListCap + i] > bk) ? 1 : 0;
-  int lo = 0, hi = kListCap;
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {          // answers 0..128: 8 halvings; empty (0) tail entries are < any key
-    const int mid = (lo + hi) >> 1;
-    if (lo < hi) { if (scr[mid] > bk) lo = mid + 1; else hi = mid; }
-  }
-  const int mypos = lo + rank_b;
-  __syncwarp();
-  if (bk != 0) scr[kListCap + rank_b] = bk;   // new keys sorted descending (keys are unique)
-  __syncwarp();
-  int l2[4] = {0, 0, 0, 0}, h2[4] = {c, c, c, c};
-#pragma unroll
-  for (int it = 0; it < 6; ++it) {           // answers 0..c, c <= 32: 6 halvings, four searches in lockstep
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int mid = (l2[r] + h2[r]) >> 1;
-      const uint64_t probe = scr[kListCap + (mid < 31 ? mid : 31)];
-      if (l2[r] < h2[r]) { if (probe > Lr[r]) l2[r] = mid + 1; else h2[r] = mid; }
-    }
-  }
-  uint64_t kth = 0;
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    if (Lr[r] != 0) {
-      const int p = lane + 32 * r + l2[r];
-      if (p < k) {
-        list[p] = Lr[r];
-        if (p == k - 1) kth = Lr[r];
-      }
-    }
-  }
-  if (bk != 0 && mypos < k) {
-    list[mypos] = bk;
-    if (mypos == k - 1) kth = bk;
-  }
-  __syncwarp();
-  const uint32_t klo = __reduce_or_sync(kFull, (uint32_t)kth);
-  const uint32_t khi = __reduce_or_sync(kFull, (uint32_t)(kth >> 32));
-  return ((uint64_t)khi << 32) | klo;
+  for (int r = 0; r < 4; ++r) list[lane + 32 * r] = Lr[r];
 }
-
-// MAXC: compile-time bound on c (24 from the append buffers, 32 in the list-merge kernel).
-// Everything is written as short independent instruction streams (broadcast shared-memory loads + compares),
-// not dependent chains: one warp per scheduler runs this, so latency, not issue rate, is what it costs.
-template <int MAXC>
-__device__ __forceinline__ uint64_t warp_merge_loaded(const uint64_t (&Lr)[4], uint64_t* list, uint64_t bk, int c, int k,
-                                                      uint64_t* scr) {
-  const int lane = threadIdx.x & 31;
-  uint32_t* scr32 = reinterpret_cast<uint32_t*>(scr + kListCap);   // reused for the insertion points below
-#pragma unroll
-  for (int r = 0; r < 4; ++r) scr[lane + 32 * r] = Lr[r];
-  scr[kListCap + lane] = bk;
-  __syncwarp();
-  // (1) rank among the new keys: #new keys larger than mine
-  int rank_b = 0;
-#pragma unroll
-  for (int i = 0; i < MAXC; ++i) rank_b += (i < c && scr[kListCap + i] > bk) ? 1 : 0;
-  // (2) insertion point in the list = #list entries larger than mine: 8 pivots (every 16th entry), then the
-  //     16 entries of the pivot's segment -- two rounds of independent loads instead of an 8-step search
-  int seg = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) seg += (scr[16 * i + 15] > bk) ? 1 : 0;   // segments entirely larger than my key
-  int lo = 16 * seg;
-  if (seg < 8) {
-    const uint64_t* sp = scr + 16 * seg;
-    int in = 0;
-#pragma unroll
-    for (int i = 0; i < 15; ++i) in += (sp[i] > bk) ? 1 : 0;             // entry 15 of the segment is <= my key
-    lo += in;
-  }
-  const int mypos = lo + rank_b;
-  __syncwarp();
-  // (3) publish insertion points; a list entry at position p moves down by #new keys with insertion point <= p
-  if (lane < c) scr32[lane] = (uint32_t)lo;
-  __syncwarp();
-  int sh0 = 0, sh1 = 0, sh2 = 0, sh3 = 0;
-#pragma unroll
-  for (int i = 0; i < MAXC; ++i) {
-    const int li = (i < c) ? (int)scr32[i] : 0x7fffffff;
-    sh0 += (li <= lane) ? 1 : 0;
-    sh1 += (li <= lane + 32) ? 1 : 0;
-    sh2 += (li <= lane + 64) ? 1 : 0;
-    sh3 += (li <= lane + 96) ? 1 : 0;
-  }
-  const int sh[4] = {sh0, sh1, sh2, sh3};
-  uint64_t kth = 0;
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    if (Lr[r] != 0) {
-      const int p = lane + 32 * r + sh[r];
-      if (p < k) {
-        list[p] = Lr[r];
-        if (p == k - 1) kth = Lr[r];
-      }
-    }
-  }
-  if (bk != 0 && mypos < k) {
-    list[mypos] = bk;
-    if (mypos == k - 1) kth = bk;
-  }
-  __syncwarp();
-  const uint32_t klo = __reduce_or_sync(kFull, (uint32_t)kth);
-  const uint32_t khi = __reduce_or_sync(kFull, (uint32_t)(kth >> 32));
-  return ((uint64_t)khi << 32) | klo;
-}
-
-__device__ __forceinline__ uint64_t warp_merge_keys(uint64_t* list, uint64_t bk, int c, int k, uint64_t* scr) {
-  uint64_t Lr[4];
-  warp_load_list(Lr, list);
-  return warp_merge_loaded_bsearch<32>(Lr, list, bk, c, k, scr);
+// key at position pos (0..127) of a striped list, broadcast to all lanes
+__device__ __forceinline__ uint64_t warp_list_at(const uint64_t (&Lr)[4], int pos) {
+  const int r = pos >> 5;
+  const uint64_t v = r == 0 ? Lr[0] : (r == 1 ? Lr[1] : (r == 2 ? Lr[2] : Lr[3]));
+  return __shfl_sync(kFull, v, pos & 31);
 }
 
 // Streaming top-k state of ONE query, owned by one thread; 32 queries (one warp) are compacted together.
@@ -197,13 +128,14 @@ struct CompactResult {
   int cnt;
   unsigned merges;
 };
+// One copy in the binary (noinline): it is called from several places of hot loops whose code must stay inside
+// the instruction cache.  Fullest buffers first, at most max_lanes of them per call (bounded work keeps the
+// epilogue's pace even); the next lane's list is prefetched from L2 while the current one is merged.
 __device__ __noinline__ CompactResult warp_compact_impl(uint64_t thr_key, int cnt, int min_cnt, int k, uint64_t* buf_warp,
-                                                        uint64_t* lists_warp, uint32_t* tau_global_warp, uint64_t* scr,
-                                                        int variant, int max_lanes) {
+                                                        uint64_t* lists_warp, uint32_t* tau_global_warp, int max_lanes) {
   TopKThread st{thr_key, cnt};
   unsigned merges = 0;
   const int lane = threadIdx.x & 31;
-  // fullest buffers first, at most max_lanes of them: bounded work per call keeps the epilogue's pace even
   int mx = __reduce_max_sync(kFull, st.cnt);
   if (mx < min_cnt || mx == 0) return CompactResult{st.thr_key, st.cnt, 0u};
   int ql = __ffs(__ballot_sync(kFull, st.cnt == mx)) - 1;
@@ -216,13 +148,13 @@ __device__ __noinline__ CompactResult warp_compact_impl(uint64_t thr_key, int cn
     uint64_t Lr[4] = {Lnext[0], Lnext[1], Lnext[2], Lnext[3]};
     if (lane == ql) st.cnt = 0;
     ++merges;
-    // pick (and prefetch) the next lane before merging this one
     mx = __reduce_max_sync(kFull, st.cnt);
     const bool more = (int)merges < max_lanes && mx >= min_cnt && mx > 0;
     const int qn = more ? __ffs(__ballot_sync(kFull, st.cnt == mx)) - 1 : 0;
     if (more) warp_load_list(Lnext, lists_warp + (size_t)qn * kListCap);
-    const uint64_t kth = variant ? warp_merge_loaded<kBufSlots>(Lr, list, bk, c, k, scr)
-                                 : warp_merge_loaded_bsearch<kBufSlots>(Lr, list, bk, c, k, scr);
+    warp_list_insert(Lr, bk);
+    warp_store_list(list, Lr);
+    const uint64_t kth = warp_list_at(Lr, k - 1);
     if (lane == ql) {
       if (kth > st.thr_key) st.thr_key = kth;
       if (tau_global_warp != nullptr && kth != 0) atomicMax(tau_global_warp + ql, (uint32_t)(kth >> 32));
@@ -234,10 +166,8 @@ __device__ __noinline__ CompactResult warp_compact_impl(uint64_t thr_key, int cn
   return CompactResult{st.thr_key, st.cnt, merges};
 }
 __device__ __forceinline__ void warp_compact(TopKThread& st, int min_cnt, int k, uint64_t* buf_warp, uint64_t* lists_warp,
-                                             uint32_t* tau_global_warp, uint64_t* scr, TopKStats& stats, int variant = 0,
-                                             int max_lanes = 32) {
-  const CompactResult r = warp_compact_impl(st.thr_key, st.cnt, min_cnt, k, buf_warp, lists_warp, tau_global_warp, scr, variant,
-                                            max_lanes);
+                                             uint32_t* tau_global_warp, TopKStats& stats, int max_lanes = 32) {
+  const CompactResult r = warp_compact_impl(st.thr_key, st.cnt, min_cnt, k, buf_warp, lists_warp, tau_global_warp, max_lanes);
   st.thr_key = r.thr_key;
   st.cnt = r.cnt;
   stats.compactions += r.merges;
