@@ -133,6 +133,12 @@ void ia_catalog_destroy(ia_catalog* cat);
 #define IA_MAX_K 128
 int ia_catalog_topk(ia_catalog* cat, int measure, const void* queries, int64_t q, int64_t ldq,
                     int k, uint64_t* keys_out, ia_stream_t stream);
+/* Same, with per-query lower bounds known to the caller: tau_init[q] (int64 holding the upper 32 bits of a key,
+ * 0 = none) promises that the final k-th best key of query q -- over ALL shards the caller will merge -- is
+ * >= tau_init[q] << 32, so candidates below it are never collected.  This is how row shards share what they
+ * learnt in a cheap probe pass (ShardedCatalogIndex: min over ranks of each rank's ceil(k/G)-th best). */
+int ia_catalog_topk_seeded(ia_catalog* cat, int measure, const void* queries, int64_t q, int64_t ldq,
+                           int k, const int64_t* tau_init, uint64_t* keys_out, ia_stream_t stream);
 /* Telemetry of the last ia_catalog_topk on this handle (synchronises the device): out8[0] keys appended to the
  * per-query buffers, [1] buffer->list merges, [2] 32-column groups that left the fast path, [3] rare-path
  * iterations, and epilogue-warp cycle sums: [4] waiting for accumulators, [5] in merges, [6] total, [7] rare path. */

@@ -43,6 +43,7 @@ SIGNATURES = {
     "ia_catalog_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "ia_catalog_destroy": (None, [c_void_p]),
     "ia_catalog_topk": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "ia_catalog_topk_seeded": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "ia_catalog_last_stats": (c_int, [c_void_p, c_void_p]),
     "ia_catalog_last_plan": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ia_topk_merge": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),

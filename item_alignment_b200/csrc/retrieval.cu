@@ -532,6 +532,13 @@ __global__ void __launch_bounds__(256) unpack_keys_kernel(const uint64_t* __rest
   }
 }
 
+// tau_global seeded from caller-provided lower bounds (goodness words held in int64), 0 = no bound
+__global__ void __launch_bounds__(256) seed_tau_kernel(const int64_t* __restrict__ init, uint32_t* __restrict__ tau, int64_t q_rows,
+                                                       int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    tau[i] = i < q_rows ? (uint32_t)(uint64_t)init[i] : 0u;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) inv_norm_rows_kernel(const T* x, int64_t n, int d, int64_t ldx, float eps, float* out) {
   const int lane = threadIdx.x & 31;
@@ -678,6 +685,11 @@ void ia_catalog_destroy(ia_catalog* cat) {
 
 int ia_catalog_topk(ia_catalog* cat, int measure, const void* queries, int64_t q, int64_t ldq, int k,
                     uint64_t* keys_out, ia_stream_t stream) {
+  return ia_catalog_topk_seeded(cat, measure, queries, q, ldq, k, nullptr, keys_out, stream);
+}
+
+int ia_catalog_topk_seeded(ia_catalog* cat, int measure, const void* queries, int64_t q, int64_t ldq, int k,
+                           const int64_t* tau_init, uint64_t* keys_out, ia_stream_t stream) {
   if (cat == nullptr || queries == nullptr || keys_out == nullptr || q < 0 || ldq < cat->d) { set_error("bad arguments"); return IA_ERR_INVALID; }
   if (measure < IA_INNER || measure > IA_L2) { set_error("Unsupported similarty measure: %d", measure); return IA_ERR_INVALID; }
   if (k < 1 || k > IA_MAX_K) { set_error("k must be in [1, %d]", IA_MAX_K); return IA_ERR_INVALID; }
@@ -711,6 +723,10 @@ int ia_catalog_topk(ia_catalog* cat, int measure, const void* queries, int64_t q
   const size_t tau_n = (size_t)p.n_qt * BM, done_n = (size_t)n_items * 4;
   if ((rc = grow((void**)&cat->tau, &cat->tau_bytes, sizeof(uint32_t) * (tau_n + done_n))) != IA_OK) return rc;
   IA_CUDA_CHECK(cudaMemsetAsync(cat->tau, 0, sizeof(uint32_t) * (tau_n + done_n), s));
+  if (tau_init != nullptr) {
+    seed_tau_kernel<<<(int)((tau_n + 255) / 256), 256, 0, s>>>(tau_init, cat->tau, q, (int64_t)tau_n);
+    IA_LAUNCH_CHECK();
+  }
   IA_CUDA_CHECK(cudaMemsetAsync(cat->stats, 0, sizeof(unsigned long long) * 8, s));
   cat->last_splits = p.n_splits; cat->last_tiles_per_split = p.tiles_per_split;
   p.lists = cat->lists; p.tau_global = cat->tau; p.done = cat->tau + tau_n; p.cinv = cat->cinv; p.stats = cat->stats;

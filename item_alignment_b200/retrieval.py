@@ -59,8 +59,9 @@ class CatalogIndex:
     def __exit__(self, *a):
         self.close()
 
-    def topk_keys(self, queries, k, measure="cosine"):
-        """[Q, k] uint64 keys (as int64 storage), best first."""
+    def topk_keys(self, queries, k, measure="cosine", init_tau=None):
+        """[Q, k] uint64 keys (as int64 storage), best first.  init_tau: optional int64 [Q] lower bounds on the final
+        k-th best key's upper word (see ia_catalog_topk_seeded); rows below them are not collected."""
         if measure not in MEASURES:
             raise ValueError(f"Unsupported similarty measure: {measure}")
         if not self._h:
@@ -72,9 +73,14 @@ class CatalogIndex:
         if queries.stride(1) != 1:
             queries = queries.contiguous()
         keys = torch.empty((queries.shape[0], k), dtype=torch.int64, device=queries.device)
+        if init_tau is not None:
+            init_tau = init_tau.to(torch.int64).contiguous()
+            if init_tau.numel() != queries.shape[0]:
+                raise ValueError("init_tau needs one entry per query")
         with torch.cuda.device(queries.device):
-            check(lib().ia_catalog_topk(self._h, MEASURES[measure], queries.data_ptr(), queries.shape[0], _ld(queries), int(k),
-                                        keys.data_ptr(), _stream()))
+            check(lib().ia_catalog_topk_seeded(self._h, MEASURES[measure], queries.data_ptr(), queries.shape[0], _ld(queries),
+                                               int(k), init_tau.data_ptr() if init_tau is not None else None,
+                                               keys.data_ptr(), _stream()))
         return keys
 
     def topk(self, queries, k, measure="cosine"):
@@ -131,7 +137,7 @@ class ShardedCatalogIndex:
     local top-k as global-row keys, ONE all-gather ([Q,k] u64 per rank) moves them over NVLink, and every rank
     merges the G lists with the same unsigned compare, so ties still break by global row."""
 
-    def __init__(self, local_catalog, total_rows, group=None):
+    def __init__(self, local_catalog, total_rows, group=None, probe_fraction=1.0 / 16):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -143,17 +149,40 @@ class ShardedCatalogIndex:
             raise ValueError(f"rank {self.rank} must hold rows [{lo}, {hi}) of the catalog, got {local_catalog.shape[0]} rows")
         self.lo, self.hi = lo, hi
         self.local = CatalogIndex(local_catalog, row_base=lo) if hi > lo else None
+        # probe = a prefix of the local shard, scanned first with k' = ceil(k/G) to agree on a global lower bound
+        self.probe = None
+        if self.world > 1 and hi > lo and probe_fraction > 0:
+            n_probe = min(hi - lo, max(4096, int((hi - lo) * probe_fraction)))
+            self.probe = CatalogIndex(local_catalog[:n_probe], row_base=lo)
 
     def close(self):
         if self.local is not None:
             self.local.close()
+        if self.probe is not None:
+            self.probe.close()
+
+    def probe_bound(self, queries, k, measure):
+        """Lower bound on every query's final k-th best key word, agreed by all ranks with ONE small all-reduce:
+        each rank reports the ceil(k/G)-th best of its probe rows; the minimum over ranks is exceeded-or-met by at
+        least G*ceil(k/G) >= k catalog rows, so nothing below it can be in the global top-k."""
+        kp = -(-k // self.world)
+        if self.probe is not None and kp <= _lib.IA_MAX_K:
+            pk = self.probe.topk_keys(queries, kp, measure)
+            words = (pk[:, kp - 1] >> 32) & 0xFFFFFFFF
+        else:
+            words = torch.zeros(queries.shape[0], dtype=torch.int64, device=queries.device)
+        self.dist.all_reduce(words, op=self.dist.ReduceOp.MIN, group=self.group)
+        return words
 
     def gather_keys(self, keys):
         return all_gather_keys(keys, self.group)
 
-    def topk_keys(self, queries, k, measure="cosine"):
+    def topk_keys(self, queries, k, measure="cosine", use_probe=True):
+        bound = None
+        if self.world > 1 and use_probe:
+            bound = self.probe_bound(queries, k, measure)
         if self.local is not None:
-            keys = self.local.topk_keys(queries, k, measure)
+            keys = self.local.topk_keys(queries, k, measure, init_tau=bound)
         else:
             keys = torch.zeros((queries.shape[0], k), dtype=torch.int64, device=queries.device)
         if self.world == 1:

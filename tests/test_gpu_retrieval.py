@@ -102,6 +102,28 @@ def test_shard_merge_equals_single_index(m, dt):
                 parts.append(shard.topk_keys(q, k, m))
         merged = ia.merge_keys(torch.stack(parts), k)
         assert torch.equal(merged, whole), f"world {world}: merged shard keys differ from the single index"
+        # the probe protocol of ShardedCatalogIndex, emulated on one GPU: every shard reports the ceil(k/G)-th best of a
+        # prefix of its rows, the minimum over shards seeds every shard's thresholds; the result must not change
+        kp = -(-k // world)
+        words = []
+        for r in range(world):
+            lo, hi = ia.shard_bounds(c_n, world, r)
+            n_probe = max(kp, (hi - lo) // 4)
+            with ia.CatalogIndex(catd[lo:lo + n_probe], row_base=lo) as probe:
+                pk = probe.topk_keys(q, kp, m)
+            words.append((pk[:, kp - 1] >> 32) & 0xFFFFFFFF)
+        bound = torch.stack(words).min(dim=0).values
+        assert int(bound.min()) > 0
+        parts = []
+        for r in range(world):
+            lo, hi = ia.shard_bounds(c_n, world, r)
+            with ia.CatalogIndex(catd[lo:hi], row_base=lo) as shard:
+                parts.append(shard.topk_keys(q, k, m, init_tau=bound))
+                seeded = shard.last_stats()["appends"]
+                shard.topk_keys(q, k, m)
+                assert seeded <= shard.last_stats()["appends"]       # the bound can only remove work
+        merged = ia.merge_keys(torch.stack(parts), k)
+        assert torch.equal(merged, whole), f"world {world}: seeded shard keys differ from the single index"
     scores, rows = ia.unpack_keys(whole, m)
     assert int(rows.max()) < c_n and int(rows.min()) >= 0
 
