@@ -34,6 +34,7 @@ struct RetrParams {
   const float* cinv;    // [c_rows] 1/max(|c|,eps)   (cosine)
   const float* qinv;    // [q_rows]                  (cosine)
   uint64_t* lists;      // [n_splits*n_qt][BM][kListCap]
+  uint64_t* overflow;   // [n_splits*n_qt][BM][kBufSlots] keys still in the append buffers when an item ended
   uint32_t* tau_global; // [n_qt*BM] best published k-th goodness per query (0 = none)
   uint32_t* done;       // [n_items*4] set when a warp's quarter of an item's lists is final
   unsigned long long* stats;  // [8] appends, compactions, rare groups, rare blocks (telemetry)
@@ -106,7 +107,9 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BUF_BYTES + CINV_BYTES + SCR_B
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 }  // namespace tc
 
-template <bool COSINE, int AB_FORMAT>
+// KREG > 0: "small k" mode (k <= KREG): every thread keeps its query's top-KREG keys sorted in REGISTERS -- no append
+// buffers, no warp merges, no lists in L2 until the item ends.  Used for k <= 16 (probe passes, top-10 workloads).
+template <bool COSINE, int AB_FORMAT, int KREG>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                    const RetrParams p) {
@@ -219,6 +222,10 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       uint32_t* tau_warp = p.tau_global + qt * BM + e * 32;
       TopKThread st{0ull, 0};
       if (p.flags & 4) st.thr_key = finished_splits_bound(p, qt, split, e, row_local, BM);
+      uint64_t top[KREG > 0 ? KREG : 1];
+#pragma unroll
+      for (int i = 0; i < (KREG > 0 ? KREG : 1); ++i) top[i] = 0ull;
+      uint32_t tau_published = 0;
 
       for (int t = t0; t < t1; ++t) {
         const int64_t j0 = (int64_t)t * BN;
@@ -282,13 +289,31 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 if (s >= thr_f && j < p.c_rows) {
                   const uint64_t key = make_key<true>(s, p.row_base + (uint32_t)j);
                   if (key > st.thr_key) {
-                    buf_warp[lane * kBufPitch + st.cnt] = key;
-                    st.cnt++;
                     stats.appends++;
+                    if (KREG > 0) {
+                      // sorted insertion into the register list (compare-exchange chain), new k-th best at once
+                      uint64_t x = key;
+                      uint64_t kth = 0;
+#pragma unroll
+                      for (int i = 0; i < KREG; ++i) {
+                        const uint64_t hi = u64max(top[i], x);
+                        x = u64min(top[i], x);
+                        top[i] = hi;
+                        if (i == p.k - 1) kth = hi;
+                      }
+                      if (kth > st.thr_key) {
+                        st.thr_key = kth;
+                        thr_f = score_of_goodness<true>((uint32_t)(kth >> 32));
+                        thr_pre = COSINE ? prefilter_threshold(thr_f, qinv) : thr_f;
+                      }
+                    } else {
+                      buf_warp[lane * kBufPitch + st.cnt] = key;
+                      st.cnt++;
+                    }
                   }
                 }
               }
-              if (__any_sync(kFull, st.cnt == kBufSlots)) {
+              if (KREG == 0 && __any_sync(kFull, st.cnt == kBufSlots)) {
                 __syncwarp();
                 const long long c0 = clock64();
                 warp_compact(st, (p.flags & 8) ? kBufSlots : kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp, stats);
@@ -312,14 +337,29 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         // list maintenance OUTSIDE the accumulator's critical section: half-full buffers are merged now, while the
         // tensor core works on the next tiles, so that buffers rarely fill up (and force a merge) mid-tile
-        if (__any_sync(kFull, st.cnt >= kBufSlots / 2)) {
+        if (KREG == 0 && __any_sync(kFull, st.cnt >= kBufSlots / 2)) {
           const long long c0 = clock64();
           warp_compact(st, kBufSlots / 2, p.k, buf_warp, lists_warp, tau_warp, stats, (p.flags & 8) ? 2 : 32);
           cyc_compact += clock64() - c0;
         }
+        if (KREG > 0) {   // publish an improved k-th best for the other CTAs working on these queries (once per tile)
+          const uint32_t w = (uint32_t)(st.thr_key >> 32);
+          // (thr_key may also hold a bound learnt from others; re-publishing that is harmless: atomicMax)
+          if (w > tau_published && q_ok) { atomicMax(tau_warp + lane, w); tau_published = w; }
+        }
       }
       __syncwarp();
-      warp_compact(st, 1, p.k, buf_warp, lists_warp, tau_warp, stats);   // flush
+      if (KREG > 0) {
+        // the register list becomes the item's list (positions >= KREG stay zero from the initialisation above)
+        uint64_t* mine = lists_warp + (size_t)lane * kListCap;
+#pragma unroll
+        for (int i = 0; i < KREG; ++i) mine[i] = top[i];
+      } else {
+        // no flush merges: the (few) keys still buffered go to the item's overflow slots; merge_lists_kernel, which
+        // has the whole GPU to itself, folds them in.  Lists stay valid lower bounds for finished_splits_bound.
+        uint64_t* ov = p.overflow + ((size_t)item * BM + row_local) * kBufSlots;
+        for (int i = 0; i < kBufSlots; ++i) ov[i] = i < st.cnt ? buf_warp[lane * kBufPitch + i] : 0ull;
+      }
       // publish: this quarter of the item's lists is final (release after every lane's list writes)
       __threadfence();
       __syncwarp();
@@ -491,7 +531,8 @@ retrieve_simt_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__
 // One warp per query: merge `parts` sorted key lists into the best k.
 //   internal layout (tile_rows > 0): list of (part, q) at src + ((part*n_qt + q/tile_rows)*tile_rows + q%tile_rows)*kListCap
 //   flat layout     (tile_rows == 0): src + (part*q_rows + q)*src_len
-__global__ void __launch_bounds__(256) merge_lists_kernel(const uint64_t* __restrict__ src, int parts, int64_t q_rows,
+__global__ void __launch_bounds__(256) merge_lists_kernel(const uint64_t* __restrict__ src,
+                                                          const uint64_t* __restrict__ overflow, int parts, int64_t q_rows,
                                                           int n_qt, int tile_rows, int src_len, int k,
                                                           uint64_t* __restrict__ out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -509,6 +550,11 @@ __global__ void __launch_bounds__(256) merge_lists_kernel(const uint64_t* __rest
         for (int r = 0; r < 4; ++r) A[r] = B[r];
       } else {
         warp_merge_lists(A, B);      // one bitonic merge per part: ~200 shuffle/compare instructions
+      }
+      if (overflow != nullptr) {     // keys that were still in the item's append buffer (unsorted, <= kBufSlots)
+        const uint64_t* ov = overflow + (((size_t)part * n_qt + (size_t)(q / tile_rows)) * tile_rows + (size_t)(q % tile_rows)) * kBufSlots;
+        const uint64_t nk = lane < kBufSlots ? __ldg(ov + lane) : 0ull;
+        if (__any_sync(kFull, nk != 0)) warp_list_insert(A, nk);
       }
     }
 #pragma unroll
@@ -713,13 +759,17 @@ int ia_catalog_topk_seeded(ia_catalog* cat, int measure, const void* queries, in
   const int sms = sm_count();
   int ctas = sms;
   if (!use_tc) ctas = sms * 2;
+  const bool use_kreg = use_tc && k <= 16;
+  // cold-start cost per item in tiles: small when the caller seeds the thresholds or the list lives in registers
   double penalty = (use_tc ? 0.3 : 0.15) * k;
+  if (use_tc && (tau_init != nullptr || use_kreg)) penalty = 2.0 + 0.03 * k;
   if (const char* f = getenv("IA_RETR_PENALTY")) penalty = atof(f) * k;
   plan_splits(p.n_qt, p.n_tiles, ctas, use_tc ? 8 : 4, penalty, &p.n_splits, &p.tiles_per_split);
   const int64_t n_items = (int64_t)p.n_qt * p.n_splits;
 
   int rc;
-  if ((rc = grow((void**)&cat->lists, &cat->lists_bytes, sizeof(uint64_t) * (size_t)n_items * BM * kListCap)) != IA_OK) return rc;
+  const size_t lists_n = (size_t)n_items * BM * kListCap, ov_n = (size_t)n_items * BM * kBufSlots;
+  if ((rc = grow((void**)&cat->lists, &cat->lists_bytes, sizeof(uint64_t) * (lists_n + ov_n))) != IA_OK) return rc;
   const size_t tau_n = (size_t)p.n_qt * BM, done_n = (size_t)n_items * 4;
   if ((rc = grow((void**)&cat->tau, &cat->tau_bytes, sizeof(uint32_t) * (tau_n + done_n))) != IA_OK) return rc;
   IA_CUDA_CHECK(cudaMemsetAsync(cat->tau, 0, sizeof(uint32_t) * (tau_n + done_n), s));
@@ -729,7 +779,7 @@ int ia_catalog_topk_seeded(ia_catalog* cat, int measure, const void* queries, in
   }
   IA_CUDA_CHECK(cudaMemsetAsync(cat->stats, 0, sizeof(unsigned long long) * 8, s));
   cat->last_splits = p.n_splits; cat->last_tiles_per_split = p.tiles_per_split;
-  p.lists = cat->lists; p.tau_global = cat->tau; p.done = cat->tau + tau_n; p.cinv = cat->cinv; p.stats = cat->stats;
+  p.lists = cat->lists; p.overflow = cat->lists + lists_n; p.tau_global = cat->tau; p.done = cat->tau + tau_n; p.cinv = cat->cinv; p.stats = cat->stats;
   if (measure == IA_COSINE) {
     if ((rc = grow((void**)&cat->qinv, &cat->qinv_bytes, sizeof(float) * (size_t)q)) != IA_OK) return rc;
     if ((rc = ia_row_inv_norm(cat->dtype, queries, q, cat->d, ldq, kCosEps, cat->qinv, stream)) != IA_OK) return rc;
@@ -745,8 +795,13 @@ int ia_catalog_topk_seeded(ia_catalog* cat, int measure, const void* queries, in
       IA_LAUNCH_CHECK();
       return IA_OK;
     };
-    if (measure == IA_COSINE) rc = fmt_bf16 ? launch(retrieve_tc_kernel<true, 1>) : launch(retrieve_tc_kernel<true, 0>);
-    else rc = fmt_bf16 ? launch(retrieve_tc_kernel<false, 1>) : launch(retrieve_tc_kernel<false, 0>);
+    if (use_kreg) {
+      if (measure == IA_COSINE) rc = fmt_bf16 ? launch(retrieve_tc_kernel<true, 1, 16>) : launch(retrieve_tc_kernel<true, 0, 16>);
+      else rc = fmt_bf16 ? launch(retrieve_tc_kernel<false, 1, 16>) : launch(retrieve_tc_kernel<false, 0, 16>);
+    } else {
+      if (measure == IA_COSINE) rc = fmt_bf16 ? launch(retrieve_tc_kernel<true, 1, 0>) : launch(retrieve_tc_kernel<true, 0, 0>);
+      else rc = fmt_bf16 ? launch(retrieve_tc_kernel<false, 1, 0>) : launch(retrieve_tc_kernel<false, 0, 0>);
+    }
     if (rc != IA_OK) return rc;
   } else {
     auto launch = [&](auto kernel, auto* tq) -> int {
@@ -771,7 +826,8 @@ int ia_catalog_topk_seeded(ia_catalog* cat, int measure, const void* queries, in
   }
   const int64_t mwant = (q + 7) / 8;
   const int mgrid = (int)(mwant < 4 * sms ? mwant : 4 * sms);
-  merge_lists_kernel<<<mgrid, 256, 0, s>>>(cat->lists, p.n_splits, q, p.n_qt, BM, kListCap, k, keys_out);
+  merge_lists_kernel<<<mgrid, 256, 0, s>>>(cat->lists, use_kreg || !use_tc ? nullptr : p.overflow, p.n_splits, q, p.n_qt, BM, kListCap, k,
+                                           keys_out);
   IA_LAUNCH_CHECK();
   return IA_OK;
 }
@@ -794,7 +850,7 @@ int ia_topk_merge(const uint64_t* keys_in, int parts, int64_t q, int k, uint64_t
   if (q == 0) return IA_OK;
   const int64_t mwant = (q + 7) / 8;
   const int mgrid = (int)(mwant < 4 * sm_count() ? mwant : 4 * sm_count());
-  merge_lists_kernel<<<mgrid, 256, 0, (cudaStream_t)stream>>>(keys_in, parts, q, 0, 0, k, k, keys_out);
+  merge_lists_kernel<<<mgrid, 256, 0, (cudaStream_t)stream>>>(keys_in, nullptr, parts, q, 0, 0, k, k, keys_out);
   IA_LAUNCH_CHECK();
   return IA_OK;
 }

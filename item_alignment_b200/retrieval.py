@@ -149,27 +149,46 @@ class ShardedCatalogIndex:
             raise ValueError(f"rank {self.rank} must hold rows [{lo}, {hi}) of the catalog, got {local_catalog.shape[0]} rows")
         self.lo, self.hi = lo, hi
         self.local = CatalogIndex(local_catalog, row_base=lo) if hi > lo else None
-        # probe = a prefix of the local shard, scanned first with k' = ceil(k/G) to agree on a global lower bound
-        self.probe = None
-        if self.world > 1 and hi > lo and probe_fraction > 0:
-            n_probe = min(hi - lo, max(4096, int((hi - lo) * probe_fraction)))
-            self.probe = CatalogIndex(local_catalog[:n_probe], row_base=lo)
+        # probes = disjoint row groups at the head of the local shard, scanned first with a small k' to agree on a
+        # global lower bound (probe_bound).  k' <= 16 keeps the probe on the kernel's register top-k path.
+        self.probe_fraction = probe_fraction
+        self.probes = []
+        self._probe_for = None
+
+    def _ensure_probes(self, k):
+        if self._probe_for == k or self.local is None or self.world == 1 or self.probe_fraction <= 0:
+            return
+        for p in self.probes:
+            p.close()
+        self.probes = []
+        rows = self.hi - self.lo
+        groups = max(1, -(-k // (16 * self.world)))
+        self.kp = -(-k // (self.world * groups))
+        per = max(2048, int(rows * self.probe_fraction) // groups)
+        if per * groups <= rows:
+            cat = self.local.catalog
+            self.probes = [CatalogIndex(cat[g * per:(g + 1) * per], row_base=self.lo + g * per) for g in range(groups)]
+        self._probe_for = k
 
     def close(self):
         if self.local is not None:
             self.local.close()
-        if self.probe is not None:
-            self.probe.close()
+        for p in self.probes:
+            p.close()
+        self.probes = []
 
     def probe_bound(self, queries, k, measure):
-        """Lower bound on every query's final k-th best key word, agreed by all ranks with ONE small all-reduce:
-        each rank reports the ceil(k/G)-th best of its probe rows; the minimum over ranks is exceeded-or-met by at
-        least G*ceil(k/G) >= k catalog rows, so nothing below it can be in the global top-k."""
-        kp = -(-k // self.world)
-        if self.probe is not None and kp <= _lib.IA_MAX_K:
-            pk = self.probe.topk_keys(queries, kp, measure)
-            words = (pk[:, kp - 1] >> 32) & 0xFFFFFFFF
-        else:
+        """Lower bound on every query's final k-th best key word, agreed by all ranks with ONE small all-reduce.
+        Every probe group (G ranks x g groups, disjoint rows) reports its k'-th best, k' = ceil(k / (G*g)); the
+        minimum over all groups is met or exceeded by at least G*g*k' >= k catalog rows, so nothing below it can be
+        in the global top-k."""
+        self._ensure_probes(k)
+        words = None
+        for p in self.probes:
+            pk = p.topk_keys(queries, self.kp, measure)
+            w = (pk[:, self.kp - 1] >> 32) & 0xFFFFFFFF
+            words = w if words is None else torch.minimum(words, w)
+        if words is None:          # no probe on this rank (tiny or empty shard): no information, no bound
             words = torch.zeros(queries.shape[0], dtype=torch.int64, device=queries.device)
         self.dist.all_reduce(words, op=self.dist.ReduceOp.MIN, group=self.group)
         return words

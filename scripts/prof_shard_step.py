@@ -13,18 +13,23 @@ rows = C // world
 cat = torch.tanh(torch.randn(rows, D, device=dev, generator=gen)).to(torch.bfloat16)
 q = torch.tanh(torch.randn(Q, D, device=dev, generator=gen)).to(torch.bfloat16)
 local = ia.CatalogIndex(cat, row_base=0)
-n_probe = min(rows, max(4096, int(rows * frac)))
-probe = ia.CatalogIndex(cat[:n_probe], row_base=0)
-kp = -(-K // world)
+groups = max(1, -(-K // (16 * world)))
+kp = -(-K // (world * groups))
+per = max(2048, int(rows * frac) // groups)
+n_probe = per * groups
+probes = [ia.CatalogIndex(cat[g * per:(g + 1) * per], row_base=g * per) for g in range(groups)]
 names = ["probe topk", "bound words", "main topk (seeded)", "fake gather+merge"]
 acc = {n: [] for n in names}
 tot = []
 for it in range(12):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     ev[0].record()
-    pk = probe.topk_keys(q, kp, "cosine")
+    pks = [pr.topk_keys(q, kp, "cosine") for pr in probes]
     ev[1].record()
-    words = (pk[:, kp - 1] >> 32) & 0xFFFFFFFF
+    words = None
+    for pk in pks:
+        wd = (pk[:, kp - 1] >> 32) & 0xFFFFFFFF
+        words = wd if words is None else torch.minimum(words, wd)
     ev[2].record()
     keys = local.topk_keys(q, K, "cosine", init_tau=words)
     ev[3].record()
@@ -37,7 +42,7 @@ for it in range(12):
             acc[n].append(ev[i].elapsed_time(ev[i + 1]))
         tot.append(ev[0].elapsed_time(ev[4]))
 st = local.last_stats()
-print(f"world={world} shard rows={rows} probe rows={n_probe} k'={kp}")
+print(f"world={world} shard rows={rows} probe rows={n_probe} in {groups} group(s) k'={kp}")
 for n in names:
     print(f"  {n:24s} {statistics.median(acc[n]):.3f} ms")
 print(f"  total {statistics.median(tot):.3f} ms; main-pass appends/query {st['appends']/Q:.0f}, merges/query {st['compactions']/Q:.1f}, splits {st['splits']}x{st['tiles_per_split']}")
