@@ -7,7 +7,10 @@
 // dx, dy are produced from the same registers and written once with 128-bit stores.
 // Algorithmic traffic: forward 2*D*e + 8 B/pair, fused forward+backward 4*D*e + 16 B/pair.
 #pragma once
+#include <cstdlib>
+
 #include "common.cuh"
+#include "ptx_sm100.cuh"   // mbarrier / bulk-copy PTX wrappers
 
 namespace ia {
 
@@ -97,7 +100,12 @@ __device__ __forceinline__ GradCoef score_grad_coef(const RowSums& s, float sim,
   return c;
 }
 
-template <typename T, typename G, int MEASURE, int MODE, bool COSLOSS, int VPL>
+// BULK: rows arrive through a per-warp shared-memory ring filled by cp.async.bulk (TMA engine, one instruction
+// per row, completion on an mbarrier): kBulkStages rows per warp are in flight at all times, independent of the
+// warp's compute / store phase and of its register budget.  Otherwise: plain 128-bit streaming loads.
+constexpr int kBulkStages = 3;
+
+template <typename T, typename G, int MEASURE, int MODE, bool COSLOSS, int VPL, bool BULK>
 __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
   constexpr int E = VecTraits<T>::kElems;
   constexpr bool kGradCosForm = COSLOSS || MEASURE == IA_INNER || MEASURE == IA_COSINE;
@@ -107,19 +115,59 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
   const int nvec = p.d / E;
   float loss_acc = 0.f;
 
-  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_in_block; row < p.n; row += warps_total) {
-    const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + row * p.ldx);
-    const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + row * p.ldy);
+  extern __shared__ __align__(128) uint8_t ring_raw[];
+  const uint32_t row_bytes = (uint32_t)p.d * (uint32_t)sizeof(T);
+  uint8_t* ring = ring_raw + (size_t)warp_in_block * kBulkStages * 2 * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_raw + (size_t)8 * kBulkStages * 2 * row_bytes) + warp_in_block * kBulkStages;
+  const int64_t row0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+  auto arm = [&](int stage, int64_t row) {   // lane 0 only
+    uint8_t* dst = ring + (size_t)stage * 2 * row_bytes;
+    mbar_arrive_expect_tx(&bars[stage], 2 * row_bytes);
+    bulk_load_1d(dst, static_cast<const T*>(p.x) + row * p.ldx, row_bytes, &bars[stage]);
+    bulk_load_1d(dst + row_bytes, static_cast<const T*>(p.y) + row * p.ldy, row_bytes, &bars[stage]);
+  };
+  if (BULK) {
+    if (lane == 0) {
+      for (int s = 0; s < kBulkStages; ++s) mbar_init(&bars[s], 1);
+      fence_mbar_init();
+      for (int s = 0; s < kBulkStages; ++s)
+        if (row0 + s * warps_total < p.n) arm(s, row0 + s * warps_total);
+    }
+    __syncwarp();
+  }
+
+  int it = 0;
+  for (int64_t row = row0; row < p.n; row += warps_total, ++it) {
     uint4 xv[VPL], yv[VPL];
+    if (BULK) {
+      const int stage = it % kBulkStages;
+      mbar_wait(&bars[stage], (uint32_t)(it / kBulkStages) & 1u);
+      const uint4* xs = reinterpret_cast<const uint4*>(ring + (size_t)stage * 2 * row_bytes);
+      const uint4* ys = reinterpret_cast<const uint4*>(ring + (size_t)stage * 2 * row_bytes + row_bytes);
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nvec) {
-        xv[i] = ldg_stream(xr + v);
-        yv[i] = ldg_stream(yr + v);
-      } else {
-        xv[i] = make_uint4(0, 0, 0, 0);
-        yv[i] = make_uint4(0, 0, 0, 0);
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) { xv[i] = xs[v]; yv[i] = ys[v]; }
+        else { xv[i] = make_uint4(0, 0, 0, 0); yv[i] = make_uint4(0, 0, 0, 0); }
+      }
+      __syncwarp();                       // every lane has its vectors in registers: the slot can be refilled
+      if (lane == 0) {
+        const int64_t next = row + (int64_t)kBulkStages * warps_total;
+        if (next < p.n) { fence_proxy_async(); arm(stage, next); }
+      }
+    } else {
+      const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + row * p.ldx);
+      const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + row * p.ldy);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) {
+          xv[i] = ldg_stream(xr + v);
+          yv[i] = ldg_stream(yr + v);
+        } else {
+          xv[i] = make_uint4(0, 0, 0, 0);
+          yv[i] = make_uint4(0, 0, 0, 0);
+        }
       }
     }
     int label = 0;
@@ -318,14 +366,52 @@ int launch_rows(const PairParams& p, cudaStream_t stream) {
   return IA_OK;
 }
 
+// bulk-ring launch: dynamic shared memory = 8 warps x kBulkStages x (x row + y row) + barriers
+template <void (*kernel)(const PairParams)>
+int launch_rows_bulk(const PairParams& p, size_t elem_size, cudaStream_t stream) {
+  constexpr int kThreads = 256, kWarps = 8;
+  const size_t smem = (size_t)kWarps * kBulkStages * 2 * (size_t)p.d * elem_size + kWarps * kBulkStages * 8;
+  static size_t configured = 0;
+  static int cached_bps = 0;
+  if (smem > configured) {
+    IA_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+    cached_bps = 0;
+  }
+  if (cached_bps == 0) cached_bps = blocks_per_sm(kernel, kThreads, smem);
+  int64_t want = (p.n + kWarps - 1) / kWarps;
+  int64_t cap = (int64_t)sm_count() * cached_bps;
+  if (cap > kMaxPartials) cap = kMaxPartials;
+  int grid = (int)(want < cap ? want : cap);
+  if (grid < 1) grid = 1;
+  kernel<<<grid, kThreads, smem, stream>>>(p);
+  IA_LAUNCH_CHECK();
+  return IA_OK;
+}
+
+inline bool pair_bulk_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("IA_PAIR_BULK");
+    on = e ? atoi(e) : 1;
+  }
+  return on != 0;
+}
+
 template <typename T, typename G, int MEASURE, int MODE, bool COSLOSS>
 int launch_pair_vpl(const PairParams& p, bool vec_ok, cudaStream_t stream) {
   constexpr int E = VecTraits<T>::kElems;
   const int nvec = p.d / E;
   if (!vec_ok || nvec > 32 * 8) return launch_rows<pair_kernel_generic<T, G, MEASURE, MODE, COSLOSS>>(p, stream);
-  if (nvec <= 64) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2>>(p, stream);
-  if (nvec <= 128) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4>>(p, stream);
-  return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8>>(p, stream);
+  // big rows (>= 1 KB) of the forward / fused kernels go through the bulk-copy ring
+  if (MODE != kModeBwd && pair_bulk_enabled() && (size_t)p.d * sizeof(T) >= 1024 && p.n >= 1024) {
+    if (nvec <= 64) return launch_rows_bulk<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2, true>>(p, sizeof(T), stream);
+    if (nvec <= 128) return launch_rows_bulk<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, true>>(p, sizeof(T), stream);
+    return launch_rows_bulk<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8, true>>(p, sizeof(T), stream);
+  }
+  if (nvec <= 64) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2, false>>(p, stream);
+  if (nvec <= 128) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, false>>(p, stream);
+  return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8, false>>(p, stream);
 }
 
 template <typename T, typename G, int MODE, bool COSLOSS>
