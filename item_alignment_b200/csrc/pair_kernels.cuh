@@ -393,7 +393,7 @@ inline bool pair_bulk_enabled() {
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("IA_PAIR_BULK");
-    on = e ? atoi(e) : 1;
+    on = e ? atoi(e) : 0;   // measured (profiles/r01/pair_configs_bulk_ab.log): direct loads win for 2 KB rows, tie for 4 KB
   }
   return on != 0;
 }
