@@ -105,8 +105,11 @@ __device__ __forceinline__ GradCoef score_grad_coef(const RowSums& s, float sim,
 // warp's compute / store phase and of its register budget.  Otherwise: plain 128-bit streaming loads.
 constexpr int kBulkStages = 3;
 
-template <typename T, typename G, int MEASURE, int MODE, bool COSLOSS, int VPL, bool BULK>
+// ROWS: pairs a warp processes per iteration (their loads are all issued up front).  2 KB rows (16-bit, D=1024)
+// use ROWS=2 so that a warp has 8 KB in flight per iteration like a 4 KB fp32 row does.
+template <typename T, typename G, int MEASURE, int MODE, bool COSLOSS, int VPL, bool BULK, int ROWS>
 __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
+  static_assert(!BULK || ROWS == 1, "the bulk ring feeds one row per iteration");
   constexpr int E = VecTraits<T>::kElems;
   constexpr bool kGradCosForm = COSLOSS || MEASURE == IA_INNER || MEASURE == IA_COSINE;
   const int lane = threadIdx.x & 31;
@@ -137,8 +140,15 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
   }
 
   int it = 0;
-  for (int64_t row = row0; row < p.n; row += warps_total, ++it) {
-    uint4 xv[VPL], yv[VPL];
+  for (int64_t rbase = row0; rbase < p.n; rbase += ROWS * warps_total, ++it) {
+    uint4 xv[ROWS][VPL], yv[ROWS][VPL];
+    bool live[ROWS];
+    int64_t rows[ROWS];
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) {
+      rows[k] = rbase + k * warps_total;
+      live[k] = rows[k] < p.n;
+    }
     if (BULK) {
       const int stage = it % kBulkStages;
       mbar_wait(&bars[stage], (uint32_t)(it / kBulkStages) & 1u);
@@ -147,109 +157,129 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
         const int v = lane + 32 * i;
-        if (v < nvec) { xv[i] = xs[v]; yv[i] = ys[v]; }
-        else { xv[i] = make_uint4(0, 0, 0, 0); yv[i] = make_uint4(0, 0, 0, 0); }
+        if (v < nvec) { xv[0][i] = xs[v]; yv[0][i] = ys[v]; }
+        else { xv[0][i] = make_uint4(0, 0, 0, 0); yv[0][i] = make_uint4(0, 0, 0, 0); }
       }
       __syncwarp();                       // every lane has its vectors in registers: the slot can be refilled
       if (lane == 0) {
-        const int64_t next = row + (int64_t)kBulkStages * warps_total;
+        const int64_t next = rbase + (int64_t)kBulkStages * warps_total;
         if (next < p.n) { fence_proxy_async(); arm(stage, next); }
       }
     } else {
-      const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + row * p.ldx);
-      const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + row * p.ldy);
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) {
-        const int v = lane + 32 * i;
-        if (v < nvec) {
-          xv[i] = ldg_stream(xr + v);
-          yv[i] = ldg_stream(yr + v);
-        } else {
-          xv[i] = make_uint4(0, 0, 0, 0);
-          yv[i] = make_uint4(0, 0, 0, 0);
+      for (int k = 0; k < ROWS; ++k) {
+        const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + rows[k] * p.ldx);
+        const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + rows[k] * p.ldy);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const int v = lane + 32 * i;
+          if (live[k] && v < nvec) {
+            xv[k][i] = ldg_stream(xr + v);
+            yv[k][i] = ldg_stream(yr + v);
+          } else {
+            xv[k][i] = make_uint4(0, 0, 0, 0);
+            yv[k][i] = make_uint4(0, 0, 0, 0);
+          }
         }
       }
     }
-    int label = 0;
-    float gup = 0.f;
-    if (MODE == kModeFused) label = (int)(__ldg(p.labels + row) != 0);
-    if (MODE == kModeBwd) gup = __ldg(p.gsim + row);
-
-    RowSums s{0.f, 0.f, 0.f, 0.f};
+    int label[ROWS];
+    float gup[ROWS];
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      if (lane + 32 * i < nvec) {   // masked lanes must not add the l1/l2 eps
-        float fx[E], fy[E];
-        unpack<T>(xv[i], fx);
-        unpack<T>(yv[i], fy);
-        accumulate<MEASURE, COSLOSS>(fx, fy, E, s);
-      }
-    }
-    if (MEASURE == IA_INNER || MEASURE == IA_COSINE || COSLOSS) s.xy = warp_sum(s.xy);
-    if (MEASURE == IA_COSINE || COSLOSS) { s.xx = warp_sum(s.xx); s.yy = warp_sum(s.yy); }
-    if (MEASURE == IA_L1 || MEASURE == IA_L2) s.dist = warp_sum(s.dist);
-
-    float nx = 1.f, ny = 1.f;
-    const float sim = score_from_sums<MEASURE>(s, nx, ny);
-
-    if (MODE != kModeBwd && lane == 0) {
-      if (p.sim) p.sim[row] = sim;
-      const float pr = prob_of<MEASURE>(sim);
-      if (p.probs) p.probs[row] = pr;
-      if (MODE == kModeFwd && p.labels_out) p.labels_out[row] = (uint8_t)((double)pr >= p.threshold);
-    }
-    if (MODE == kModeFwd) continue;
-
-    GradCoef c;
-    if (MODE == kModeFused) {
-      float li, g;
-      if (COSLOSS) {
-        // nn.CosineEmbeddingLoss (text.py:1401,1471): c = xy / sqrt((xx+eps)(yy+eps))
-        const float a = s.xx + kCosEmbEps, b = s.yy + kCosEmbEps;
-        const float den = sqrtf(a * b);
-        const float cs = s.xy / den;
-        float gc;
-        if (label) { li = 1.f - cs; gc = -1.f; }
-        else { li = fmaxf(0.f, cs - p.margin); gc = (cs - p.margin) > 0.f ? 1.f : 0.f; }
-        gc *= p.grad_scale;
-        c.A = gc / den; c.Bx = gc * cs / a; c.By = gc * cs / b;
-      } else {
-        li = scalar_loss(p.loss, sim, label, p.margin, g);
-        c = score_grad_coef<MEASURE>(s, sim, nx, ny, g * p.grad_scale);
-      }
-      if (p.reduction == IA_RED_NONE) { if (lane == 0) p.loss_out[row] = li; }
-      else loss_acc += li;
-    } else {
-      c = score_grad_coef<MEASURE>(s, sim, nx, ny, gup);
+    for (int k = 0; k < ROWS; ++k) {
+      label[k] = 0;
+      gup[k] = 0.f;
+      if (MODE == kModeFused && live[k]) label[k] = (int)(__ldg(p.labels + rows[k]) != 0);
+      if (MODE == kModeBwd && live[k]) gup[k] = __ldg(p.gsim + rows[k]);
     }
 
-    if (p.dx != nullptr) {
-      G* dxr = static_cast<G*>(p.dx) + row * p.lddx;
-      G* dyr = static_cast<G*>(p.dy) + row * p.lddy;
+    RowSums s[ROWS];
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) {
+      s[k] = RowSums{0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
-        const int v = lane + 32 * i;
-        if (v < nvec) {
-          float fx[E], fy[E], gx[E], gy[E];
-          unpack<T>(xv[i], fx);
-          unpack<T>(yv[i], fy);
+        if (lane + 32 * i < nvec) {   // masked lanes must not add the l1/l2 eps
+          float fx[E], fy[E];
+          unpack<T>(xv[k][i], fx);
+          unpack<T>(yv[k][i], fy);
+          accumulate<MEASURE, COSLOSS>(fx, fy, E, s[k]);
+        }
+      }
+    }
 #pragma unroll
-          for (int j = 0; j < E; ++j) {
-            if (kGradCosForm) {
-              gx[j] = c.A * fy[j] - c.Bx * fx[j];
-              gy[j] = c.A * fx[j] - c.By * fy[j];
-            } else if (MEASURE == IA_L1) {
-              const float dd = fx[j] - fy[j] + kPdistEps;
-              gx[j] = dd > 0.f ? c.A : (dd < 0.f ? -c.A : 0.f);
-              gy[j] = -gx[j];
-            } else {
-              const float dd = fx[j] - fy[j] + kPdistEps;
-              gx[j] = c.A * dd;
-              gy[j] = -gx[j];
+    for (int k = 0; k < ROWS; ++k) {
+      if (MEASURE == IA_INNER || MEASURE == IA_COSINE || COSLOSS) s[k].xy = warp_sum(s[k].xy);
+      if (MEASURE == IA_COSINE || COSLOSS) { s[k].xx = warp_sum(s[k].xx); s[k].yy = warp_sum(s[k].yy); }
+      if (MEASURE == IA_L1 || MEASURE == IA_L2) s[k].dist = warp_sum(s[k].dist);
+    }
+
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) {
+      if (!live[k]) continue;
+      const int64_t row = rows[k];
+      float nx = 1.f, ny = 1.f;
+      const float sim = score_from_sums<MEASURE>(s[k], nx, ny);
+
+      if (MODE != kModeBwd && lane == 0) {
+        if (p.sim) p.sim[row] = sim;
+        const float pr = prob_of<MEASURE>(sim);
+        if (p.probs) p.probs[row] = pr;
+        if (MODE == kModeFwd && p.labels_out) p.labels_out[row] = (uint8_t)((double)pr >= p.threshold);
+      }
+      if (MODE == kModeFwd) continue;
+
+      GradCoef c;
+      if (MODE == kModeFused) {
+        float li, g;
+        if (COSLOSS) {
+          // nn.CosineEmbeddingLoss (text.py:1401,1471): c = xy / sqrt((xx+eps)(yy+eps))
+          const float a = s[k].xx + kCosEmbEps, b = s[k].yy + kCosEmbEps;
+          const float den = sqrtf(a * b);
+          const float cs = s[k].xy / den;
+          float gc;
+          if (label[k]) { li = 1.f - cs; gc = -1.f; }
+          else { li = fmaxf(0.f, cs - p.margin); gc = (cs - p.margin) > 0.f ? 1.f : 0.f; }
+          gc *= p.grad_scale;
+          c.A = gc / den; c.Bx = gc * cs / a; c.By = gc * cs / b;
+        } else {
+          li = scalar_loss(p.loss, sim, label[k], p.margin, g);
+          c = score_grad_coef<MEASURE>(s[k], sim, nx, ny, g * p.grad_scale);
+        }
+        if (p.reduction == IA_RED_NONE) { if (lane == 0) p.loss_out[row] = li; }
+        else loss_acc += li;
+      } else {
+        c = score_grad_coef<MEASURE>(s[k], sim, nx, ny, gup[k]);
+      }
+
+      if (p.dx != nullptr) {
+        G* dxr = static_cast<G*>(p.dx) + row * p.lddx;
+        G* dyr = static_cast<G*>(p.dy) + row * p.lddy;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const int v = lane + 32 * i;
+          if (v < nvec) {
+            float fx[E], fy[E], gx[E], gy[E];
+            unpack<T>(xv[k][i], fx);
+            unpack<T>(yv[k][i], fy);
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+              if (kGradCosForm) {
+                gx[j] = c.A * fy[j] - c.Bx * fx[j];
+                gy[j] = c.A * fx[j] - c.By * fy[j];
+              } else if (MEASURE == IA_L1) {
+                const float dd = fx[j] - fy[j] + kPdistEps;
+                gx[j] = dd > 0.f ? c.A : (dd < 0.f ? -c.A : 0.f);
+                gy[j] = -gx[j];
+              } else {
+                const float dd = fx[j] - fy[j] + kPdistEps;
+                gx[j] = c.A * dd;
+                gy[j] = -gx[j];
+              }
             }
+            Packer<G, E>::store(dxr + (int64_t)v * E, gx);
+            Packer<G, E>::store(dyr + (int64_t)v * E, gy);
           }
-          Packer<G, E>::store(dxr + (int64_t)v * E, gx);
-          Packer<G, E>::store(dyr + (int64_t)v * E, gy);
         }
       }
     }
@@ -398,6 +428,15 @@ inline bool pair_bulk_enabled() {
   return on != 0;
 }
 
+inline bool pair_rows2_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("IA_PAIR_ROWS2");
+    on = e ? atoi(e) : 1;
+  }
+  return on != 0;
+}
+
 template <typename T, typename G, int MEASURE, int MODE, bool COSLOSS>
 int launch_pair_vpl(const PairParams& p, bool vec_ok, cudaStream_t stream) {
   constexpr int E = VecTraits<T>::kElems;
@@ -405,13 +444,17 @@ int launch_pair_vpl(const PairParams& p, bool vec_ok, cudaStream_t stream) {
   if (!vec_ok || nvec > 32 * 8) return launch_rows<pair_kernel_generic<T, G, MEASURE, MODE, COSLOSS>>(p, stream);
   // big rows (>= 1 KB) of the forward / fused kernels go through the bulk-copy ring
   if (MODE != kModeBwd && pair_bulk_enabled() && (size_t)p.d * sizeof(T) >= 1024 && p.n >= 1024) {
-    if (nvec <= 64) return launch_rows_bulk<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2, true>>(p, sizeof(T), stream);
-    if (nvec <= 128) return launch_rows_bulk<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, true>>(p, sizeof(T), stream);
-    return launch_rows_bulk<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8, true>>(p, sizeof(T), stream);
+    if (nvec <= 64) return launch_rows_bulk<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2, true, 1>>(p, sizeof(T), stream);
+    if (nvec <= 128) return launch_rows_bulk<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, true, 1>>(p, sizeof(T), stream);
+    return launch_rows_bulk<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8, true, 1>>(p, sizeof(T), stream);
   }
-  if (nvec <= 64) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2, false>>(p, stream);
-  if (nvec <= 128) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, false>>(p, stream);
-  return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8, false>>(p, stream);
+  if (nvec <= 64) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2, false, 1>>(p, stream);
+  if (nvec <= 128) {
+    // two pairs per warp iteration once the batch is large enough to keep every warp busy with pairs of rows
+    if (pair_rows2_enabled() && p.n >= 16384) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, false, 2>>(p, stream);
+    return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, false, 1>>(p, stream);
+  }
+  return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8, false, 1>>(p, stream);
 }
 
 template <typename T, typename G, int MODE, bool COSLOSS>

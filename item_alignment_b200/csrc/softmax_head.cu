@@ -10,6 +10,7 @@
 // Two classes: delta = p1 - label is formed without cancellation (label 1 -> -p0), dlogit1 = delta,
 // dlogit0 = -delta, so dW[0] = -dW[1] and db[0] = -db[1].
 #include "common.cuh"
+#include "ptx_sm100.cuh"
 
 namespace ia {
 
@@ -31,26 +32,74 @@ struct HeadParams {
   float grad_scale;   // upstream / n
   double loss_scale;  // 1/n
   void* workspace;    // [kWorkspaceBytes | float partial[grid][2h+2]]
+  int stages;         // ring depth (TRAIN)
 };
 
 constexpr int kHeadMaxGrid = 592;  // 148 SMs x 4
 
+// Shared-memory layout of one weight-row half (h floats): "lane-interleaved chunks" -- the float4 a lane needs for
+// input vector v = lane + 32*i, chunk q sits at float4 index (i*(E/4)+q)*32 + lane, so every LDS.128 of a warp
+// covers 512 contiguous bytes (conflict free).
+template <int E>
+__device__ __forceinline__ int swz(int e) {
+  const int v = e / E, j = e % E;
+  return (((v >> 5) * (E / 4) + (j >> 2)) * 32 + (v & 31)) * 4 + (j & 3);
+}
+
+constexpr int kHeadMaxStages = 4;   // rows in flight per warp in the bulk-copy ring (TRAIN kernel), fewer if smem is short
+
+// TRAIN keeps 2*VPL*E dW accumulators per lane in registers, which limits it to one CTA (8 warps) per SM: the
+// rows therefore arrive through a per-warp shared-memory ring filled by cp.async.bulk (p.stages rows in flight
+// per warp regardless of registers).  The forward-only kernel is light and uses plain streaming loads.
 template <typename T, typename G, bool TRAIN, int VPL>
 __global__ void __launch_bounds__(256) softmax_head_kernel(const HeadParams p) {
   constexpr int E = VecTraits<T>::kElems;
-  extern __shared__ float smem[];
-  float* sw = smem;                 // [2][2h]
-  float* sacc = smem + 4 * p.h;     // [2h] block accumulator of dW[1] (TRAIN)
+  constexpr int C = E / 4;            // float4 chunks per 128-bit input vector
+  constexpr int P4 = VPL * 32 * C;    // float4 per (padded) weight-row half
+  extern __shared__ float4 smem4[];
+  // [w0x | w0y | w1x | w1y | (TRAIN) wdx | wdy | sacc[2h] | ring | barriers]
+  const float4* w0x = smem4;
+  const float4* w0y = smem4 + P4;
+  const float4* w1x = smem4 + 2 * P4;
+  const float4* w1y = smem4 + 3 * P4;
+  const float4* wdx = smem4 + 4 * P4;
+  const float4* wdy = smem4 + 5 * P4;
+  float* sw = reinterpret_cast<float*>(smem4);
+  float* sacc = sw + 24 * P4;
   const int h = p.h, h2 = 2 * p.h;
-  for (int i = threadIdx.x; i < 2 * h2; i += blockDim.x) sw[i] = p.w[i];
-  if (TRAIN)
-    for (int i = threadIdx.x; i < h2; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
-  const float b0 = p.b[0], b1 = p.b[1];
-
+  for (int i = threadIdx.x; i < h2; i += blockDim.x) {
+    const int half = i >= h, e = half ? i - h : i;
+    const int pos = half * (4 * P4) + swz<E>(e);
+    const float a = p.w[i], c = p.w[h2 + i];
+    sw[pos] = a;
+    sw[8 * P4 + pos] = c;
+    if (TRAIN) { sw[16 * P4 + pos] = c - a; sacc[i] = 0.f; }
+  }
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warps_total = (int64_t)gridDim.x * 8;
   const int nvec = h / E;
+  const uint32_t row_bytes = (uint32_t)h * (uint32_t)sizeof(T);
+  uint8_t* ring_base = reinterpret_cast<uint8_t*>(sacc + ((h2 + 3) & ~3));
+  uint8_t* ring = ring_base + (size_t)wib * p.stages * 2 * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_base + (size_t)8 * p.stages * 2 * row_bytes) + wib * p.stages;
+  const int64_t row0 = (int64_t)blockIdx.x * 8 + wib;
+  auto arm = [&](int stage, int64_t row) {   // lane 0 only
+    uint8_t* dst = ring + (size_t)stage * 2 * row_bytes;
+    mbar_arrive_expect_tx(&bars[stage], 2 * row_bytes);
+    bulk_load_1d(dst, static_cast<const T*>(p.x) + row * p.ldx, row_bytes, &bars[stage]);
+    bulk_load_1d(dst + row_bytes, static_cast<const T*>(p.y) + row * p.ldy, row_bytes, &bars[stage]);
+  };
+  if (TRAIN) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) mbar_init(&bars[s], 1);
+      fence_mbar_init();
+      for (int s = 0; s < p.stages; ++s)
+        if (row0 + s * warps_total < p.n) arm(s, row0 + s * warps_total);
+    }
+  }
+  __syncthreads();
+  const float b0 = p.b[0], b1 = p.b[1];
+
   float accx[TRAIN ? VPL * E : 1], accy[TRAIN ? VPL * E : 1];
   if (TRAIN) {
 #pragma unroll
@@ -58,38 +107,61 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const HeadParams p) {
   }
   float loss_acc = 0.f, db_acc = 0.f;
 
-  for (int64_t row = (int64_t)blockIdx.x * 8 + wib; row < p.n; row += warps_total) {
-    const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + row * p.ldx);
-    const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + row * p.ldy);
+  int it = 0;
+  for (int64_t row = row0; row < p.n; row += warps_total, ++it) {
     uint4 xv[VPL], yv[VPL];
+    if (TRAIN) {
+      const int stage = it % p.stages;
+      mbar_wait(&bars[stage], (uint32_t)(it / p.stages) & 1u);
+      const uint4* xs = reinterpret_cast<const uint4*>(ring + (size_t)stage * 2 * row_bytes);
+      const uint4* ys = reinterpret_cast<const uint4*>(ring + (size_t)stage * 2 * row_bytes + row_bytes);
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nvec) { xv[i] = ldg_stream(xr + v); yv[i] = ldg_stream(yr + v); }
-      else { xv[i] = make_uint4(0, 0, 0, 0); yv[i] = make_uint4(0, 0, 0, 0); }
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) { xv[i] = xs[v]; yv[i] = ys[v]; }
+        else { xv[i] = make_uint4(0, 0, 0, 0); yv[i] = make_uint4(0, 0, 0, 0); }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        const int64_t next = row + (int64_t)p.stages * warps_total;
+        if (next < p.n) { fence_proxy_async(); arm(stage, next); }
+      }
+    } else {
+      const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + row * p.ldx);
+      const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + row * p.ldy);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) { xv[i] = ldg_stream(xr + v); yv[i] = ldg_stream(yr + v); }
+        else { xv[i] = make_uint4(0, 0, 0, 0); yv[i] = make_uint4(0, 0, 0, 0); }
+      }
     }
     int label = 0;
     if (TRAIN) label = (int)(__ldg(p.labels + row) != 0);
-    float l0 = 0.f, l1 = 0.f;
+    float l0x = 0.f, l0y = 0.f, l1x = 0.f, l1y = 0.f;     // four independent FMA chains
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nvec) {
+      if (lane + 32 * i < nvec) {
         float fx[E], fy[E];
         unpack<T>(xv[i], fx);
         unpack<T>(yv[i], fy);
-        const int c = v * E;
 #pragma unroll
-        for (int j = 0; j < E; ++j) {
-          l0 = fmaf(fx[j], sw[c + j], l0);
-          l0 = fmaf(fy[j], sw[h + c + j], l0);
-          l1 = fmaf(fx[j], sw[h2 + c + j], l1);
-          l1 = fmaf(fy[j], sw[h2 + h + c + j], l1);
+        for (int q = 0; q < C; ++q) {
+          const int f4 = (i * C + q) * 32 + lane;
+          const float4 a0 = w0x[f4], a1 = w0y[f4], c0 = w1x[f4], c1 = w1y[f4];
+          l0x = fmaf(fx[4 * q + 0], a0.x, l0x); l0x = fmaf(fx[4 * q + 1], a0.y, l0x);
+          l0x = fmaf(fx[4 * q + 2], a0.z, l0x); l0x = fmaf(fx[4 * q + 3], a0.w, l0x);
+          l0y = fmaf(fy[4 * q + 0], a1.x, l0y); l0y = fmaf(fy[4 * q + 1], a1.y, l0y);
+          l0y = fmaf(fy[4 * q + 2], a1.z, l0y); l0y = fmaf(fy[4 * q + 3], a1.w, l0y);
+          l1x = fmaf(fx[4 * q + 0], c0.x, l1x); l1x = fmaf(fx[4 * q + 1], c0.y, l1x);
+          l1x = fmaf(fx[4 * q + 2], c0.z, l1x); l1x = fmaf(fx[4 * q + 3], c0.w, l1x);
+          l1y = fmaf(fy[4 * q + 0], c1.x, l1y); l1y = fmaf(fy[4 * q + 1], c1.y, l1y);
+          l1y = fmaf(fy[4 * q + 2], c1.z, l1y); l1y = fmaf(fy[4 * q + 3], c1.w, l1y);
         }
       }
     }
-    l0 = warp_sum(l0) + b0;
-    l1 = warp_sum(l1) + b1;
+    const float l0 = warp_sum(l0x + l0y) + b0;
+    const float l1 = warp_sum(l1x + l1y) + b1;
     const float m = fmaxf(l0, l1);
     const float e0 = expf(l0 - m), e1 = expf(l1 - m);
     const float den = e0 + e1;
@@ -103,7 +175,7 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const HeadParams p) {
     const float delta = (label ? -p0 : p1) * p.grad_scale;   // d loss / d logit1 ( = -d loss / d logit0 )
     db_acc += delta;
     G* dxr = p.dx ? static_cast<G*>(p.dx) + row * p.lddx : nullptr;
-    G* dyr = p.dy ? static_cast<G*>(p.dy) + row * p.lddy : nullptr;
+    G* dyr = p.dx ? static_cast<G*>(p.dy) + row * p.lddy : nullptr;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int v = lane + 32 * i;
@@ -111,13 +183,17 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const HeadParams p) {
         float fx[E], fy[E], gx[E], gy[E];
         unpack<T>(xv[i], fx);
         unpack<T>(yv[i], fy);
-        const int c = v * E;
+#pragma unroll
+        for (int q = 0; q < C; ++q) {
+          const int f4 = (i * C + q) * 32 + lane;
+          const float4 d0 = wdx[f4], d1 = wdy[f4];
+          gx[4 * q + 0] = delta * d0.x; gx[4 * q + 1] = delta * d0.y; gx[4 * q + 2] = delta * d0.z; gx[4 * q + 3] = delta * d0.w;
+          gy[4 * q + 0] = delta * d1.x; gy[4 * q + 1] = delta * d1.y; gy[4 * q + 2] = delta * d1.z; gy[4 * q + 3] = delta * d1.w;
+        }
 #pragma unroll
         for (int j = 0; j < E; ++j) {
           accx[i * E + j] = fmaf(delta, fx[j], accx[i * E + j]);
           accy[i * E + j] = fmaf(delta, fy[j], accy[i * E + j]);
-          gx[j] = delta * (sw[h2 + c + j] - sw[c + j]);
-          gy[j] = delta * (sw[h2 + h + c + j] - sw[h + c + j]);
         }
         if (dxr) {
           Packer<G, E>::store(dxr + (int64_t)v * E, gx);
@@ -176,9 +252,18 @@ __global__ void __launch_bounds__(256) softmax_head_finalize(const float* partia
 }
 
 template <typename T, typename G, bool TRAIN, int VPL>
-static int launch_head_one(const HeadParams& p, cudaStream_t stream, float* dw, float* db) {
+static int launch_head_one(const HeadParams& p_in, cudaStream_t stream, float* dw, float* db) {
   auto kernel = softmax_head_kernel<T, G, TRAIN, VPL>;
-  const size_t smem = sizeof(float) * (TRAIN ? 6 : 4) * p.h;
+  constexpr int P4 = VPL * 32 * (VecTraits<T>::kElems / 4);
+  const size_t w_bytes = (size_t)(TRAIN ? 6 : 4) * P4 * 16;
+  HeadParams p = p_in;
+  const size_t fixed = w_bytes + (size_t)(((2 * p.h + 3) & ~3)) * 4;
+  const size_t per_stage = (size_t)8 * 2 * p.h * sizeof(T) + 8 * 8;
+  int stages = kHeadMaxStages;
+  while (stages > 1 && fixed + stages * per_stage > 227 * 1024) --stages;
+  p.stages = stages;
+  const size_t smem = TRAIN ? fixed + stages * per_stage : w_bytes;
+  if (smem > 227 * 1024) { set_error("h too large for the shared-memory W tile + row ring"); return IA_ERR_UNSUPPORTED; }
   static bool configured = false;
   static int bps = 0;
   static size_t configured_smem = 0;
@@ -251,7 +336,6 @@ int ia_softmax_head_fwd_bwd(int dtype, int grad_dtype, const void* x, const void
     set_error("softmax head kernel needs 16-byte aligned rows, h %% %d == 0 and h <= %d", elems, 256 * elems);
     return IA_ERR_UNSUPPORTED;
   }
-  if (6 * h * sizeof(float) > 200 * 1024) { set_error("h too large for the shared-memory W tile"); return IA_ERR_UNSUPPORTED; }
   if (n == 0) {
     if (train) {
       const float v = __builtin_nanf("");
