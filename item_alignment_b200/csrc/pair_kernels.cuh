@@ -38,6 +38,7 @@ struct PairParams {
   float grad_scale;            // upstream * (1/n for mean)
   double loss_scale;           // 1/n for mean, 1 otherwise
   void* workspace;
+  int flags;                   // experiments: bit0 st.global.cs for gradients, bit1 ld.global.cs for inputs
 };
 
 // Per-pair sums gathered in one sweep over the registers.
@@ -174,8 +175,8 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
         for (int i = 0; i < VPL; ++i) {
           const int v = lane + 32 * i;
           if (live[k] && v < nvec) {
-            xv[k][i] = ldg_stream(xr + v);
-            yv[k][i] = ldg_stream(yr + v);
+            if (p.flags & 2) { xv[k][i] = ldg_cs(xr + v); yv[k][i] = ldg_cs(yr + v); }
+            else { xv[k][i] = ldg_stream(xr + v); yv[k][i] = ldg_stream(yr + v); }
           } else {
             xv[k][i] = make_uint4(0, 0, 0, 0);
             yv[k][i] = make_uint4(0, 0, 0, 0);
@@ -277,8 +278,8 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
                 gy[j] = -gx[j];
               }
             }
-            Packer<G, E>::store(dxr + (int64_t)v * E, gx);
-            Packer<G, E>::store(dyr + (int64_t)v * E, gy);
+            Packer<G, E>::store(dxr + (int64_t)v * E, gx, p.flags & 1);
+            Packer<G, E>::store(dyr + (int64_t)v * E, gy, p.flags & 1);
           }
         }
       }
