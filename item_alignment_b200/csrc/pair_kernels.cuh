@@ -141,13 +141,15 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
   }
 
   int it = 0;
-  for (int64_t rbase = row0; rbase < p.n; rbase += ROWS * warps_total, ++it) {
+  // a warp owns ROWS ADJACENT pairs per iteration (their rows are contiguous in memory when ld == d)
+  const int64_t n_super = (p.n + ROWS - 1) / ROWS;
+  for (int64_t rbase = row0; rbase < n_super; rbase += warps_total, ++it) {
     uint4 xv[ROWS][VPL], yv[ROWS][VPL];
     bool live[ROWS];
     int64_t rows[ROWS];
 #pragma unroll
     for (int k = 0; k < ROWS; ++k) {
-      rows[k] = rbase + k * warps_total;
+      rows[k] = rbase * ROWS + k;
       live[k] = rows[k] < p.n;
     }
     if (BULK) {
