@@ -431,13 +431,15 @@ inline bool pair_bulk_enabled() {
   return on != 0;
 }
 
-inline bool pair_rows2_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("IA_PAIR_ROWS2");
-    on = e ? atoi(e) : 0;   // measured (profiles/r01/pair_configs_rows2_ab.log): one row per iteration is ~1 % faster
+// IA_PAIR_ROWS: 1 = one pair per warp iteration, 4 (default) = group rows up to 8 vectors per lane,
+// 8 = group up to 16 vectors per lane (experiment)
+inline int pair_rows_pref() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IA_PAIR_ROWS");
+    v = e ? atoi(e) : 4;
   }
-  return on != 0;
+  return v;
 }
 
 template <typename T, typename G, int MEASURE, int MODE, bool COSLOSS>
@@ -451,12 +453,22 @@ int launch_pair_vpl(const PairParams& p, bool vec_ok, cudaStream_t stream) {
     if (nvec <= 128) return launch_rows_bulk<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, true, 1>>(p, sizeof(T), stream);
     return launch_rows_bulk<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8, true, 1>>(p, sizeof(T), stream);
   }
-  if (nvec <= 64) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2, false, 1>>(p, stream);
+  // ROWS adjacent pairs per warp iteration: contiguous chunks of ROWS * row_bytes per tensor.  Measured on B200
+  // (profiles/r01/pair_rows_ab.log): 4 KB chunks beat 2 KB chunks by ~7 % (DRAM page locality), so rows are
+  // grouped until VPL * ROWS == 8 vectors per lane (64 data registers) once the batch can feed every warp.
+  const int rows_pref = pair_rows_pref();
+  const bool big = p.n >= 16384;
+  if (nvec <= 64) {
+    if (big && rows_pref >= 4) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2, false, 4>>(p, stream);
+    if (big && rows_pref >= 2) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2, false, 2>>(p, stream);
+    return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2, false, 1>>(p, stream);
+  }
   if (nvec <= 128) {
-    // two pairs per warp iteration once the batch is large enough to keep every warp busy with pairs of rows
-    if (pair_rows2_enabled() && p.n >= 16384) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, false, 2>>(p, stream);
+    if (big && rows_pref >= 8) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, false, 4>>(p, stream);
+    if (big && rows_pref >= 2) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, false, 2>>(p, stream);
     return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, false, 1>>(p, stream);
   }
+  if (big && rows_pref >= 8) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8, false, 2>>(p, stream);
   return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8, false, 1>>(p, stream);
 }
 
