@@ -431,13 +431,12 @@ inline bool pair_bulk_enabled() {
   return on != 0;
 }
 
-// IA_PAIR_ROWS: 1 = one pair per warp iteration, 4 (default) = group rows up to 8 vectors per lane,
-// 8 = group up to 16 vectors per lane (experiment)
+// IA_PAIR_ROWS: 1 = one pair per warp iteration; default = group adjacent rows (see launch_pair_vpl)
 inline int pair_rows_pref() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("IA_PAIR_ROWS");
-    v = e ? atoi(e) : 4;
+    v = e ? atoi(e) : 2;
   }
   return v;
 }
@@ -453,22 +452,21 @@ int launch_pair_vpl(const PairParams& p, bool vec_ok, cudaStream_t stream) {
     if (nvec <= 128) return launch_rows_bulk<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, true, 1>>(p, sizeof(T), stream);
     return launch_rows_bulk<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8, true, 1>>(p, sizeof(T), stream);
   }
-  // ROWS adjacent pairs per warp iteration: contiguous chunks of ROWS * row_bytes per tensor.  Measured on B200
-  // (profiles/r01/pair_rows_ab.log): 4 KB chunks beat 2 KB chunks by ~7 % (DRAM page locality), so rows are
-  // grouped until VPL * ROWS == 8 vectors per lane (64 data registers) once the batch can feed every warp.
-  const int rows_pref = pair_rows_pref();
-  const bool big = p.n >= 16384;
+  // ROWS adjacent pairs per warp iteration: one contiguous chunk of ROWS * row_bytes per tensor.  Measured on B200
+  // (profiles/r01/pair_rows_ab.log): chunks of 4-6 KB stream best -- 2 KB rows (bf16 D=1024) gain 7 % when paired,
+  // 3 KB rows (fp32 D=768) gain 6 %, 4 KB rows are best alone, and 8+ KB per lane-iteration loses to register
+  // pressure.  IA_PAIR_ROWS=1 turns the grouping off.
+  const size_t row_bytes = (size_t)p.d * sizeof(T);
+  const bool group = pair_rows_pref() > 1 && p.n >= 16384;
   if (nvec <= 64) {
-    if (big && rows_pref >= 4) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2, false, 4>>(p, stream);
-    if (big && rows_pref >= 2) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2, false, 2>>(p, stream);
+    if (group && row_bytes >= 512) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2, false, 2>>(p, stream);
     return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2, false, 1>>(p, stream);
   }
   if (nvec <= 128) {
-    if (big && rows_pref >= 8) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, false, 4>>(p, stream);
-    if (big && rows_pref >= 2) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, false, 2>>(p, stream);
+    if (group) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, false, 2>>(p, stream);
     return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, false, 1>>(p, stream);
   }
-  if (big && rows_pref >= 8) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8, false, 2>>(p, stream);
+  if (group && row_bytes <= 3072) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8, false, 2>>(p, stream);
   return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8, false, 1>>(p, stream);
 }
 
