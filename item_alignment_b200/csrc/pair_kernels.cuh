@@ -453,20 +453,17 @@ int launch_pair_vpl(const PairParams& p, bool vec_ok, cudaStream_t stream) {
     return launch_rows_bulk<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8, true, 1>>(p, sizeof(T), stream);
   }
   // ROWS adjacent pairs per warp iteration: one contiguous chunk of ROWS * row_bytes per tensor.  Measured on B200
-  // (profiles/r01/pair_rows_ab.log): chunks of 4-6 KB stream best -- 2 KB rows (bf16 D=1024) gain 7 % when paired,
-  // 3 KB rows (fp32 D=768) gain 6 %, 4 KB rows are best alone, and 8+ KB per lane-iteration loses to register
-  // pressure.  IA_PAIR_ROWS=1 turns the grouping off.
+  // (profiles/r01/pair_rows_ab.log), kernels that also write gradients: 2 KB rows (bf16 D=1024) gain 7 % when paired
+  // (84.6 -> 91 % of the copy peak), 3 KB rows (fp32 D=768) gain 6 %; 1 KB rows and 4 KB rows are best alone, as is
+  // the forward-only kernel (already at the read-only peak).  IA_PAIR_ROWS=1 turns the grouping off.
   const size_t row_bytes = (size_t)p.d * sizeof(T);
-  const bool group = pair_rows_pref() > 1 && p.n >= 16384;
-  if (nvec <= 64) {
-    if (group && row_bytes >= 512) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2, false, 2>>(p, stream);
-    return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2, false, 1>>(p, stream);
-  }
+  const bool group = MODE != kModeFwd && pair_rows_pref() > 1 && p.n >= 16384 && row_bytes >= 1536 && row_bytes <= 3072;
+  if (nvec <= 64) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2, false, 1>>(p, stream);
   if (nvec <= 128) {
     if (group) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, false, 2>>(p, stream);
     return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, false, 1>>(p, stream);
   }
-  if (group && row_bytes <= 3072) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8, false, 2>>(p, stream);
+  if (group) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8, false, 2>>(p, stream);
   return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8, false, 1>>(p, stream);
 }
 
