@@ -33,6 +33,7 @@ struct HeadParams {
   double loss_scale;  // 1/n
   void* workspace;    // [kWorkspaceBytes | float partial[grid][2h+2]]
   int stages;         // ring depth (TRAIN)
+  int group;          // adjacent pairs per ring stage (TRAIN): 2 for rows <= 3 KB, else 1
 };
 
 constexpr int kHeadMaxGrid = 592;  // 148 SMs x 4
@@ -80,21 +81,28 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const HeadParams p) {
   const int nvec = h / E;
   const uint32_t row_bytes = (uint32_t)h * (uint32_t)sizeof(T);
   uint8_t* ring_base = reinterpret_cast<uint8_t*>(sacc + ((h2 + 3) & ~3));
-  uint8_t* ring = ring_base + (size_t)wib * p.stages * 2 * row_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_base + (size_t)8 * p.stages * 2 * row_bytes) + wib * p.stages;
-  const int64_t row0 = (int64_t)blockIdx.x * 8 + wib;
-  auto arm = [&](int stage, int64_t row) {   // lane 0 only
-    uint8_t* dst = ring + (size_t)stage * 2 * row_bytes;
-    mbar_arrive_expect_tx(&bars[stage], 2 * row_bytes);
-    bulk_load_1d(dst, static_cast<const T*>(p.x) + row * p.ldx, row_bytes, &bars[stage]);
-    bulk_load_1d(dst + row_bytes, static_cast<const T*>(p.y) + row * p.ldy, row_bytes, &bars[stage]);
+  const int R = p.group;                                  // adjacent pairs per stage
+  const size_t stage_bytes = (size_t)R * 2 * row_bytes;   // [x rows | y rows]
+  uint8_t* ring = ring_base + (size_t)wib * p.stages * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_base + (size_t)8 * p.stages * stage_bytes) + wib * p.stages;
+  const int64_t row0 = (int64_t)blockIdx.x * 8 + wib;     // index of the warp's first row GROUP
+  const int64_t n_groups = (p.n + R - 1) / R;
+  auto arm = [&](int stage, int64_t grp) {   // lane 0 only
+    uint8_t* dst = ring + (size_t)stage * stage_bytes;
+    const int64_t r0 = grp * R;
+    const int live = (int)((p.n - r0) < R ? (p.n - r0) : R);
+    mbar_arrive_expect_tx(&bars[stage], (uint32_t)(live * 2 * row_bytes));
+    for (int k = 0; k < live; ++k) {
+      bulk_load_1d(dst + (size_t)k * row_bytes, static_cast<const T*>(p.x) + (r0 + k) * p.ldx, row_bytes, &bars[stage]);
+      bulk_load_1d(dst + (size_t)(R + k) * row_bytes, static_cast<const T*>(p.y) + (r0 + k) * p.ldy, row_bytes, &bars[stage]);
+    }
   };
   if (TRAIN) {
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) mbar_init(&bars[s], 1);
       fence_mbar_init();
       for (int s = 0; s < p.stages; ++s)
-        if (row0 + s * warps_total < p.n) arm(s, row0 + s * warps_total);
+        if (row0 + s * warps_total < n_groups) arm(s, row0 + s * warps_total);
     }
   }
   __syncthreads();
@@ -108,23 +116,29 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const HeadParams p) {
   float loss_acc = 0.f, db_acc = 0.f;
 
   int it = 0;
-  for (int64_t row = row0; row < p.n; row += warps_total, ++it) {
+  const int64_t n_iter_items = TRAIN ? n_groups : p.n;
+  for (int64_t item = row0; item < n_iter_items; item += warps_total, ++it) {
+   const int stage = TRAIN ? it % p.stages : 0;
+   if (TRAIN) mbar_wait(&bars[stage], (uint32_t)(it / p.stages) & 1u);
+   const int live_rows = TRAIN ? (int)((p.n - item * R) < R ? (p.n - item * R) : R) : 1;
+   for (int k = 0; k < live_rows; ++k) {
+    const int64_t row = TRAIN ? item * R + k : item;
     uint4 xv[VPL], yv[VPL];
     if (TRAIN) {
-      const int stage = it % p.stages;
-      mbar_wait(&bars[stage], (uint32_t)(it / p.stages) & 1u);
-      const uint4* xs = reinterpret_cast<const uint4*>(ring + (size_t)stage * 2 * row_bytes);
-      const uint4* ys = reinterpret_cast<const uint4*>(ring + (size_t)stage * 2 * row_bytes + row_bytes);
+      const uint4* xs = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_bytes + (size_t)k * row_bytes);
+      const uint4* ys = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_bytes + (size_t)(R + k) * row_bytes);
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
         const int v = lane + 32 * i;
         if (v < nvec) { xv[i] = xs[v]; yv[i] = ys[v]; }
         else { xv[i] = make_uint4(0, 0, 0, 0); yv[i] = make_uint4(0, 0, 0, 0); }
       }
-      __syncwarp();
-      if (lane == 0) {
-        const int64_t next = row + (int64_t)p.stages * warps_total;
-        if (next < p.n) { fence_proxy_async(); arm(stage, next); }
+      if (k == live_rows - 1) {          // the whole stage is in registers / consumed: refill it
+        __syncwarp();
+        if (lane == 0) {
+          const int64_t next = item + (int64_t)p.stages * warps_total;
+          if (next < n_groups) { fence_proxy_async(); arm(stage, next); }
+        }
       }
     } else {
       const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + row * p.ldx);
@@ -201,6 +215,7 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const HeadParams p) {
         }
       }
     }
+   }   // rows of the stage
   }
 
   if (TRAIN) {
@@ -258,7 +273,9 @@ static int launch_head_one(const HeadParams& p_in, cudaStream_t stream, float* d
   const size_t w_bytes = (size_t)(TRAIN ? 6 : 4) * P4 * 16;
   HeadParams p = p_in;
   const size_t fixed = w_bytes + (size_t)(((2 * p.h + 3) & ~3)) * 4;
-  const size_t per_stage = (size_t)8 * 2 * p.h * sizeof(T) + 8 * 8;
+  const size_t row_bytes = (size_t)p.h * sizeof(T);
+  p.group = (row_bytes >= 1536 && row_bytes <= 3072 && p.n >= 16384) ? 2 : 1;   // 4-6 KB chunks stream best (see pair kernel)
+  const size_t per_stage = (size_t)8 * p.group * 2 * row_bytes + 8 * 8;
   int stages = kHeadMaxStages;
   while (stages > 1 && fixed + stages * per_stage > 227 * 1024) --stages;
   p.stages = stages;
@@ -273,7 +290,7 @@ static int launch_head_one(const HeadParams& p_in, cudaStream_t stream, float* d
     configured = true;
     configured_smem = smem;
   }
-  int64_t want = (p.n + 7) / 8;
+  int64_t want = (p.n / (TRAIN ? p.group : 1) + 7) / 8;
   int64_t cap = (int64_t)sm_count() * bps;
   if (cap > kHeadMaxGrid) cap = kHeadMaxGrid;
   const int grid = (int)(want < cap ? want : cap);
