@@ -85,6 +85,28 @@ int ia_pair_score_bwd(int measure, int dtype, int grad_dtype, const void* x, con
                       int64_t ldx, int64_t ldy, const float* gsim, int64_t n, int64_t d, void* dx,
                       void* dy, int64_t lddx, int64_t lddy, ia_stream_t stream);
 
+/* ---- gather-and-score: pair r = (row xi[r] of ex, row yi[r] of ey) --------------------------------
+ * Replaces the per-pair Python loop of GCNTwoTower.forward (src/models/graph.py:87-117: one head call per pair,
+ * torch.cat per iteration) and scores id pairs (item_train_pair.jsonl) straight against an embedding matrix such
+ * as pred_text.py:158-192's feature_matrix.  ex and ey may be the same matrix.  Gradients come back dense per pair
+ * ([n, d]); the caller scatters them into the embedding matrix gradient (index_add). */
+int ia_pair_score_gather_fwd(int measure, int dtype, const void* ex, const void* ey, int64_t rows_x,
+                             int64_t rows_y, int64_t ldx, int64_t ldy, const int64_t* xi, const int64_t* yi,
+                             int64_t n, int64_t d, float* sim, float* probs, double threshold,
+                             uint8_t* labels_out, ia_stream_t stream);
+int ia_pair_score_gather_loss_fwd_bwd(int measure, int loss, float margin, int reduction, int dtype,
+                                      int grad_dtype, const void* ex, const void* ey, int64_t ldx, int64_t ldy,
+                                      const int64_t* xi, const int64_t* yi, const int64_t* labels, int64_t n,
+                                      int64_t d, float* sim, float* probs, float* loss_out, void* dx, void* dy,
+                                      int64_t lddx, int64_t lddy, float grad_scale, void* workspace,
+                                      size_t workspace_bytes, ia_stream_t stream);
+
+/* ---- threshold sweep: confusion counts of `probs >= thresholds[k]` vs labels, k < nthr <= 32 ----------
+ * Replaces the numpy/sklearn loop of finetune_text.py:576-580 (np.arange(0.1, 1.0, 0.1); fp32 probs compared in
+ * double).  counts: [nthr][4] u64 = tp, fp, fn, tn; precision/recall/F1 follow on the host from the integers. */
+int ia_threshold_sweep(const float* probs, const int64_t* labels, int64_t n, const double* thresholds,
+                       int nthr, uint64_t* counts, ia_stream_t stream);
+
 /* ---- elementwise losses on a score vector (the reference's loss modules on their own) ---------
  * HingeLoss.forward (loss.py:126-134), EuclideanDistanceLoss.forward (loss.py:61-68), BCEWithLogits
  * (text.py:1403).  target_pm1: int64 in {-1,+1} for hinge / euclidean, {0,1} for bce.

@@ -136,6 +136,50 @@ __global__ void __launch_bounds__(256) row_inv_norm_kernel(const T* x, int64_t n
   }
 }
 
+// Confusion counts of `probs >= thr` against {0,1} labels for up to 32 thresholds at once (the sweep of
+// reference finetune_text.py:576-580).  counts: [T][4] = tp, fp, fn, tn (u64, integer atomics: deterministic).
+__global__ void __launch_bounds__(256) threshold_sweep_kernel(const float* __restrict__ probs, const int64_t* __restrict__ labels,
+                                                              int64_t n, const double* __restrict__ thr, int nthr,
+                                                              unsigned long long* __restrict__ counts) {
+  __shared__ unsigned long long sc[32][4];
+  for (int i = threadIdx.x; i < 32 * 4; i += blockDim.x) (&sc[0][0])[i] = 0ull;
+  __syncthreads();
+  double t[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) t[k] = k < nthr ? thr[k] : 0.0;
+  unsigned tp[32], pp[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) { tp[k] = 0; pp[k] = 0; }
+  unsigned pos = 0, seen = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double p = (double)probs[i];
+    const unsigned l = labels[i] != 0;
+    pos += l; ++seen;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const unsigned pred = (k < nthr) && (p >= t[k]);
+      pp[k] += pred;
+      tp[k] += pred & l;
+    }
+  }
+  for (int k = 0; k < nthr; ++k) {
+    const unsigned a = __reduce_add_sync(0xffffffffu, tp[k]);
+    const unsigned b = __reduce_add_sync(0xffffffffu, pp[k]);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&sc[k][0], (unsigned long long)a); atomicAdd(&sc[k][1], (unsigned long long)b); }
+  }
+  const unsigned ps = __reduce_add_sync(0xffffffffu, pos), ss = __reduce_add_sync(0xffffffffu, seen);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&sc[0][2], (unsigned long long)ps); atomicAdd(&sc[0][3], (unsigned long long)ss); }
+  __syncthreads();
+  if (threadIdx.x < nthr) {
+    const int k = threadIdx.x;
+    const unsigned long long tpk = sc[k][0], ppk = sc[k][1], posb = sc[0][2], seenb = sc[0][3];
+    atomicAdd(&counts[k * 4 + 0], tpk);                       // tp
+    atomicAdd(&counts[k * 4 + 1], ppk - tpk);                 // fp
+    atomicAdd(&counts[k * 4 + 2], posb - tpk);                // fn
+    atomicAdd(&counts[k * 4 + 3], (seenb - posb) - (ppk - tpk));   // tn
+  }
+}
+
 }  // namespace ia
 
 using namespace ia;
@@ -206,6 +250,63 @@ int ia_pair_score_bwd(int measure, int dtype, int grad_dtype, const void* x, con
   p.x = x; p.y = y; p.ldx = ldx; p.ldy = ldy; p.gsim = gsim; p.n = n; p.d = (int)d;
   p.dx = dx; p.dy = dy; p.lddx = lddx; p.lddy = lddy;
   return dispatch_pair(kModeBwd, false, measure, dtype, grad_dtype, p, (cudaStream_t)stream);
+}
+
+int ia_pair_score_gather_fwd(int measure, int dtype, const void* ex, const void* ey, int64_t rows_x, int64_t rows_y,
+                             int64_t ldx, int64_t ldy, const int64_t* xi, const int64_t* yi, int64_t n, int64_t d,
+                             float* sim, float* probs, double threshold, uint8_t* labels_out, ia_stream_t stream) {
+  int rc = check_common(measure, dtype, ex, ey, n, d, ldx, ldy);
+  if (rc != IA_OK) return rc;
+  if (n > 0 && (xi == nullptr || yi == nullptr || rows_x <= 0 || rows_y <= 0)) { set_error("gather needs both index arrays and the row counts"); return IA_ERR_INVALID; }
+  if (n == 0) return IA_OK;
+  PairParams p{};
+  p.x = ex; p.y = ey; p.ldx = ldx; p.ldy = ldy; p.xi = xi; p.yi = yi; p.n = n; p.d = (int)d;
+  p.sim = sim; p.probs = probs; p.labels_out = labels_out; p.threshold = threshold;
+  return dispatch_pair(kModeFwd, false, measure, dtype, dtype, p, (cudaStream_t)stream);
+}
+
+int ia_pair_score_gather_loss_fwd_bwd(int measure, int loss, float margin, int reduction, int dtype, int grad_dtype,
+                                      const void* ex, const void* ey, int64_t ldx, int64_t ldy, const int64_t* xi,
+                                      const int64_t* yi, const int64_t* labels, int64_t n, int64_t d, float* sim,
+                                      float* probs, float* loss_out, void* dx, void* dy, int64_t lddx, int64_t lddy,
+                                      float grad_scale, void* workspace, size_t workspace_bytes, ia_stream_t stream) {
+  int rc = check_common(measure, dtype, ex, ey, n, d, ldx, ldy);
+  if (rc != IA_OK) return rc;
+  if (loss < IA_LOSS_BCE || loss > IA_LOSS_COSINE) { set_error("unsupported loss_type %d", loss); return IA_ERR_INVALID; }
+  if (reduction != IA_RED_MEAN && reduction != IA_RED_SUM) { set_error("gather entry point supports mean / sum reduction"); return IA_ERR_INVALID; }
+  if (grad_dtype != dtype && grad_dtype != IA_F32) { set_error("grad_dtype must equal dtype or be fp32"); return IA_ERR_UNSUPPORTED; }
+  if ((dx == nullptr) != (dy == nullptr)) { set_error("dx and dy must both be given or both be NULL"); return IA_ERR_INVALID; }
+  if (loss_out == nullptr || (n > 0 && (labels == nullptr || xi == nullptr || yi == nullptr))) { set_error("loss_out / labels / indices must not be NULL"); return IA_ERR_INVALID; }
+  if (workspace == nullptr || workspace_bytes < kWorkspaceBytes) { set_error("workspace too small: need %zu bytes", kWorkspaceBytes); return IA_ERR_WORKSPACE; }
+  if (n == 0) {
+    const float v = reduction == IA_RED_MEAN ? __builtin_nanf("") : 0.f;
+    IA_CUDA_CHECK(cudaMemcpyAsync(loss_out, &v, sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return IA_OK;
+  }
+  PairParams p{};
+  p.x = ex; p.y = ey; p.ldx = ldx; p.ldy = ldy; p.xi = xi; p.yi = yi; p.labels = labels; p.n = n; p.d = (int)d;
+  p.sim = sim; p.probs = probs; p.loss_out = loss_out; p.dx = dx; p.dy = dy; p.lddx = lddx; p.lddy = lddy;
+  p.loss = loss; p.margin = margin; p.reduction = reduction;
+  p.loss_scale = reduction == IA_RED_MEAN ? 1.0 / (double)n : 1.0;
+  p.grad_scale = reduction == IA_RED_MEAN ? (float)((double)grad_scale / (double)n) : grad_scale;
+  p.workspace = workspace;
+  return dispatch_pair(kModeFused, loss == IA_LOSS_COSINE, measure, dtype, grad_dtype, p, (cudaStream_t)stream);
+}
+
+int ia_threshold_sweep(const float* probs, const int64_t* labels, int64_t n, const double* thresholds, int nthr,
+                       uint64_t* counts, ia_stream_t stream) {
+  if (n < 0 || nthr < 1 || nthr > 32 || counts == nullptr || thresholds == nullptr || (n > 0 && (probs == nullptr || labels == nullptr))) {
+    set_error("bad arguments (1..32 thresholds)");
+    return IA_ERR_INVALID;
+  }
+  IA_CUDA_CHECK(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * 4 * nthr, (cudaStream_t)stream));
+  if (n == 0) return IA_OK;
+  int64_t want = (n + 255) / 256;
+  int grid = (int)(want < 4 * sm_count() ? want : 4 * sm_count());
+  threshold_sweep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(probs, labels, n, thresholds, nthr,
+                                                                 reinterpret_cast<unsigned long long*>(counts));
+  IA_LAUNCH_CHECK();
+  return IA_OK;
 }
 
 int ia_score_loss_fwd_bwd(int loss, float margin, int reduction, const float* sim, const int64_t* target, int64_t n,

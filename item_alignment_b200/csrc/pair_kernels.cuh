@@ -20,6 +20,8 @@ struct PairParams {
   const void* x;
   const void* y;
   int64_t ldx, ldy;            // elements
+  const int64_t* xi;           // optional gather: pair r reads row xi[r] of x (and yi[r] of y); null = row r
+  const int64_t* yi;
   const int64_t* labels;       // fused
   const float* gsim;           // bwd
   int64_t n;
@@ -126,9 +128,10 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
   const int64_t row0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
   auto arm = [&](int stage, int64_t row) {   // lane 0 only
     uint8_t* dst = ring + (size_t)stage * 2 * row_bytes;
+    const int64_t rx = p.xi ? __ldg(p.xi + row) : row, ry = p.yi ? __ldg(p.yi + row) : row;
     mbar_arrive_expect_tx(&bars[stage], 2 * row_bytes);
-    bulk_load_1d(dst, static_cast<const T*>(p.x) + row * p.ldx, row_bytes, &bars[stage]);
-    bulk_load_1d(dst + row_bytes, static_cast<const T*>(p.y) + row * p.ldy, row_bytes, &bars[stage]);
+    bulk_load_1d(dst, static_cast<const T*>(p.x) + rx * p.ldx, row_bytes, &bars[stage]);
+    bulk_load_1d(dst + row_bytes, static_cast<const T*>(p.y) + ry * p.ldy, row_bytes, &bars[stage]);
   };
   if (BULK) {
     if (lane == 0) {
@@ -171,8 +174,10 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
     } else {
 #pragma unroll
       for (int k = 0; k < ROWS; ++k) {
-        const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + rows[k] * p.ldx);
-        const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + rows[k] * p.ldy);
+        const int64_t rx = (p.xi && live[k]) ? __ldg(p.xi + rows[k]) : rows[k];
+        const int64_t ry = (p.yi && live[k]) ? __ldg(p.yi + rows[k]) : rows[k];
+        const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + rx * p.ldx);
+        const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + ry * p.ldy);
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
           const int v = lane + 32 * i;
@@ -311,8 +316,8 @@ __global__ void __launch_bounds__(256) pair_kernel_generic(const PairParams p) {
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   float loss_acc = 0.f;
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_in_block; row < p.n; row += warps_total) {
-    const T* xr = static_cast<const T*>(p.x) + row * p.ldx;
-    const T* yr = static_cast<const T*>(p.y) + row * p.ldy;
+    const T* xr = static_cast<const T*>(p.x) + (p.xi ? __ldg(p.xi + row) : row) * p.ldx;
+    const T* yr = static_cast<const T*>(p.y) + (p.yi ? __ldg(p.yi + row) : row) * p.ldy;
     RowSums s{0.f, 0.f, 0.f, 0.f};
     for (int j = lane; j < p.d; j += 32) {
       const float fx = to_float<T>(xr[j]), fy = to_float<T>(yr[j]);
@@ -457,7 +462,8 @@ int launch_pair_vpl(const PairParams& p, bool vec_ok, cudaStream_t stream) {
   // (84.6 -> 91 % of the copy peak), 3 KB rows (fp32 D=768) gain 6 %; 1 KB rows and 4 KB rows are best alone, as is
   // the forward-only kernel (already at the read-only peak).  IA_PAIR_ROWS=1 turns the grouping off.
   const size_t row_bytes = (size_t)p.d * sizeof(T);
-  const bool group = MODE != kModeFwd && pair_rows_pref() > 1 && p.n >= 16384 && row_bytes >= 1536 && row_bytes <= 3072;
+  const bool group = MODE != kModeFwd && pair_rows_pref() > 1 && p.n >= 16384 && row_bytes >= 1536 && row_bytes <= 3072 &&
+                     p.xi == nullptr && p.yi == nullptr;   // gathered rows are not adjacent in memory
   if (nvec <= 64) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2, false, 1>>(p, stream);
   if (nvec <= 128) {
     if (group) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, false, 2>>(p, stream);

@@ -170,6 +170,117 @@ def softmax_head_raw(x, y, w, b, labels=None, grad_dtype=None, want_grads=True, 
     return logits, probs, (loss[0] if train else None), dx, dy, dw, db
 
 
+# ------------------------------------------------------------------------------------------- gather-and-score
+def _prep_gather(emb_x, emb_y, src_idx, tgt_idx):
+    if not (emb_x.is_cuda and emb_y.is_cuda):
+        raise RuntimeError("item_alignment_b200 runs on CUDA tensors only (no CPU fallback)")
+    if emb_x.dim() != 2 or emb_y.dim() != 2 or emb_x.shape[1] != emb_y.shape[1] or emb_x.dtype != emb_y.dtype:
+        raise ValueError("expected two [M, D] embedding matrices of equal D and dtype")
+    if emb_x.dtype not in _DT:
+        raise NotImplementedError(f"unsupported dtype {emb_x.dtype}")
+    if emb_x.stride(1) != 1:
+        emb_x = emb_x.contiguous()
+    if emb_y.stride(1) != 1:
+        emb_y = emb_y.contiguous()
+    src_idx = src_idx.to(device=emb_x.device, dtype=torch.int64).contiguous().view(-1)
+    tgt_idx = tgt_idx.to(device=emb_x.device, dtype=torch.int64).contiguous().view(-1)
+    if src_idx.numel() != tgt_idx.numel():
+        raise ValueError("src_idx and tgt_idx must have the same length")
+    return emb_x, emb_y, src_idx, tgt_idx
+
+
+def pair_score_gather_raw(measure, emb_x, emb_y, src_idx, tgt_idx, threshold=None):
+    """Scores of pairs given as row indices into embedding matrices, one launch (replaces the per-pair loop of
+    reference src/models/graph.py:87-117).  Returns sim, probs, labels-or-None.  Indices must be in range."""
+    emb_x, emb_y, src_idx, tgt_idx = _prep_gather(emb_x, emb_y, src_idx, tgt_idx)
+    n, d = src_idx.numel(), emb_x.shape[1]
+    dev = emb_x.device
+    sim = torch.empty(n, dtype=torch.float32, device=dev)
+    probs = torch.empty(n, dtype=torch.float32, device=dev)
+    labels = torch.empty(n, dtype=torch.bool, device=dev) if threshold is not None else None
+    with torch.cuda.device(dev):
+        check(lib().ia_pair_score_gather_fwd(_measure_id(measure), _DT[emb_x.dtype], emb_x.data_ptr(), emb_y.data_ptr(),
+                                             emb_x.shape[0], emb_y.shape[0], _ld(emb_x), _ld(emb_y), src_idx.data_ptr(),
+                                             tgt_idx.data_ptr(), n, d, sim.data_ptr(), probs.data_ptr(),
+                                             float(threshold) if threshold is not None else 0.0,
+                                             labels.data_ptr() if labels is not None else None, _stream()))
+    return sim, probs, labels
+
+
+def pair_score_loss_gather_raw(measure, loss_type, emb_x, emb_y, src_idx, tgt_idx, labels, margin=1.0, reduction="mean",
+                               grad_dtype=None, want_grads=True):
+    """Fused gather + score + loss + backward; dx, dy are dense per pair ([n, D])."""
+    emb_x, emb_y, src_idx, tgt_idx = _prep_gather(emb_x, emb_y, src_idx, tgt_idx)
+    n, d = src_idx.numel(), emb_x.shape[1]
+    dev = emb_x.device
+    if loss_type not in LOSSES:
+        raise ValueError(f"unsupported loss_type for a vector-similarity head: {loss_type}")
+    labels = labels.view(-1).to(torch.int64).contiguous()
+    gd = grad_dtype or emb_x.dtype
+    sim = torch.empty(n, dtype=torch.float32, device=dev)
+    probs = torch.empty(n, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    dx = torch.empty((n, d), dtype=gd, device=dev) if want_grads else None
+    dy = torch.empty((n, d), dtype=gd, device=dev) if want_grads else None
+    with torch.cuda.device(dev):
+        ws = workspace(dev)
+        check(lib().ia_pair_score_gather_loss_fwd_bwd(
+            _measure_id(measure), LOSSES[loss_type], float(margin), REDUCTIONS[reduction], _DT[emb_x.dtype], _DT[gd],
+            emb_x.data_ptr(), emb_y.data_ptr(), _ld(emb_x), _ld(emb_y), src_idx.data_ptr(), tgt_idx.data_ptr(),
+            labels.data_ptr(), n, d, sim.data_ptr(), probs.data_ptr(), loss.data_ptr(),
+            dx.data_ptr() if want_grads else None, dy.data_ptr() if want_grads else None, d, d, 1.0, ws.data_ptr(),
+            ws.numel(), _stream()))
+    return sim, probs, loss[0], dx, dy
+
+
+class _GatherPairLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, emb_x, emb_y, src_idx, tgt_idx, labels, measure, loss_type, margin, reduction):
+        need = emb_x.requires_grad or emb_y.requires_grad
+        sim, probs, loss, dx, dy = pair_score_loss_gather_raw(measure, loss_type, emb_x, emb_y, src_idx, tgt_idx, labels, margin,
+                                                              reduction, want_grads=need)
+        if need:
+            ctx.save_for_backward(dx, dy, src_idx, tgt_idx)
+        ctx.shapes = (emb_x.shape, emb_y.shape, emb_x.dtype, emb_y.dtype)
+        ctx.mark_non_differentiable(sim, probs)
+        return loss, sim, probs
+
+    @staticmethod
+    def backward(ctx, gloss, _gs, _gp):
+        dx, dy, src_idx, tgt_idx = ctx.saved_tensors
+        scale_inplace_(dx, dy, gloss)
+        sx, sy, tx, ty = ctx.shapes
+        gx = torch.zeros(sx, dtype=torch.float32, device=dx.device).index_add_(0, src_idx, dx.float()).to(tx)
+        gy = torch.zeros(sy, dtype=torch.float32, device=dy.device).index_add_(0, tgt_idx, dy.float()).to(ty)
+        return gx, gy, None, None, None, None, None, None, None
+
+
+def pair_score_loss_gather(measure, loss_type, emb_x, emb_y, src_idx, tgt_idx, labels, margin=1.0, reduction="mean"):
+    """(sim, probs, loss) for index pairs; loss.backward() scatters the per-pair gradients into the embedding
+    matrices' gradients (index_add)."""
+    loss, sim, probs = _GatherPairLossFn.apply(emb_x, emb_y, src_idx.to(emb_x.device).long().view(-1),
+                                               tgt_idx.to(emb_x.device).long().view(-1), labels, measure, loss_type,
+                                               float(margin), reduction)
+    return sim, probs, loss
+
+
+# ------------------------------------------------------------------------------------------- evaluation sweep
+def threshold_sweep_counts(probs, labels, thresholds):
+    """[T, 4] int64 confusion counts (tp, fp, fn, tn) of `probs >= thresholds[k]` (reference finetune_text.py:576-580)."""
+    if not probs.is_cuda:
+        raise RuntimeError("item_alignment_b200 runs on CUDA tensors only (no CPU fallback)")
+    probs = probs.detach().to(torch.float32).contiguous().view(-1)
+    labels = labels.to(device=probs.device, dtype=torch.int64).contiguous().view(-1)
+    thr = torch.as_tensor([float(t) for t in thresholds], dtype=torch.float64, device=probs.device)
+    if thr.numel() < 1 or thr.numel() > 32:
+        raise ValueError("1..32 thresholds per sweep")
+    counts = torch.empty((thr.numel(), 4), dtype=torch.int64, device=probs.device)
+    with torch.cuda.device(probs.device):
+        check(lib().ia_threshold_sweep(probs.data_ptr(), labels.data_ptr(), probs.numel(), thr.data_ptr(), thr.numel(),
+                                       counts.data_ptr(), _stream()))
+    return counts
+
+
 def row_inv_norm(x, eps=1e-8):
     if x.stride(1) != 1:
         x = x.contiguous()

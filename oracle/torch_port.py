@@ -204,3 +204,67 @@ def compute_inner(item_emb_1, item_emb_2, bias=0.0):
         s += a * b
     s += bias
     return s
+
+
+# --------------------------------------------------------------------------- evaluation sweep / threshold search
+def threshold_sweep(probs, labels, thresholds):
+    """finetune_text.py:576-580: sklearn precision / recall / f1 of `model_probs >= threshold` per threshold."""
+    import numpy as np
+    from sklearn.metrics import f1_score, precision_score, recall_score
+    import warnings
+    probs = np.asarray(probs, dtype=np.float32)
+    labels = np.asarray(labels)
+    p, r, f = [], [], []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for threshold in thresholds:
+            pred = probs >= threshold
+            p.append(precision_score(labels, pred)); r.append(recall_score(labels, pred)); f.append(f1_score(labels, pred))
+    return np.array(p), np.array(r), np.array(f)
+
+
+def find_best_f1_and_threshold(scores, labels, high_score_more_similar=True):
+    """finetune_bert.py:72-106, restated loop for loop."""
+    assert len(scores) == len(labels)
+    rows = sorted(zip(scores, labels), key=lambda x: x[0], reverse=high_score_more_similar)
+    best_f1 = best_precision = best_recall = best_acc = 0
+    threshold = 0
+    nextract = ncorrect = fneg = 0
+    total_num_duplicates = sum(labels)
+    neg_total = len(labels) - total_num_duplicates
+    for i in range(len(rows) - 1):
+        score, label = rows[i]
+        nextract += 1
+        if label == 1:
+            ncorrect += 1
+        else:
+            fneg += 1
+        if ncorrect > 0:
+            precision = ncorrect / nextract
+            recall = ncorrect / total_num_duplicates
+            f1 = 2 * precision * recall / (precision + recall)
+            acc = (ncorrect + neg_total - fneg) / len(labels)
+            if f1 > best_f1:
+                best_f1, best_precision, best_recall = f1, precision, recall
+                threshold = (rows[i][0] + rows[i + 1][0]) / 2
+                best_acc = acc
+    return best_acc, best_f1, best_precision, best_recall, threshold
+
+
+def gcn_pair_loop(measure, node_embeddings, pairs, loss_type=None, margin=1.0):
+    """The per-pair loop of GCNTwoTower.forward (src/models/graph.py:87-117) with a vector-similarity head in place of
+    the cls head: one head call per pair, concatenation per iteration, summed per-pair losses divided by len(pairs)."""
+    sims, probs_all, loss = [], [], None
+    for pair in pairs:
+        x = node_embeddings[pair["src_idx"]].unsqueeze(0).float()
+        y = node_embeddings[pair["tgt_idx"]].unsqueeze(0).float()
+        sim = similarity(measure, x, y)
+        sims.append(sim)
+        probs_all.append(probs_of(measure, sim))
+        if loss_type is not None and pair.get("item_label") is not None:
+            lab = torch.tensor([int(pair["item_label"])], dtype=torch.long)
+            li = loss_ladder(loss_type, sim, x, y, lab, margin)
+            loss = li if loss is None else loss + li
+    if loss is not None:
+        loss = loss / len(pairs)
+    return torch.cat(sims), torch.cat(probs_all), loss

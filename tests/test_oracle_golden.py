@@ -189,3 +189,16 @@ def test_live_reference_cross_check():
         assert torch.equal(sim, torch_port.similarity(m, x, y))
         assert torch.equal(rl.HingeLoss(0.7)(sim, t), torch_port.hinge_loss(sim, t, 0.7))
         assert torch.equal(rl.EuclideanDistanceLoss()(sim, t), torch_port.euclidean_loss(sim, t))
+
+
+def test_eval_restatements_small_cases():
+    """finetune_bert.py:72-106 and finetune_text.py:576-580 restatements on hand-checkable inputs."""
+    scores = [0.9, 0.8, 0.7, 0.6, 0.5, 0.4]
+    labels = [1, 1, 0, 1, 0, 0]
+    acc, f1, p, r, thr = torch_port.find_best_f1_and_threshold(scores, labels)
+    assert (p, r) == (0.75, 1.0) and abs(f1 - 6 / 7) < 1e-15 and abs(thr - 0.55) < 1e-15 and abs(acc - 5 / 6) < 1e-15
+    pr, rc, f = torch_port.threshold_sweep(np.array([0.2, 0.6, 0.7, 0.1], dtype=np.float32), np.array([0, 1, 0, 1]), [0.5])
+    assert (pr[0], rc[0], f[0]) == (0.5, 0.5, 0.5)
+    sims, probs, loss = torch_port.gcn_pair_loop("cosine", torch.eye(3), [dict(src_idx=0, tgt_idx=0, item_label=1),
+                                                                         dict(src_idx=0, tgt_idx=1, item_label=0)], "hinge", 1.0)
+    assert sims.tolist() == [1.0, 0.0] and probs.tolist() == [1.0, 0.5] and float(loss) == 0.5
