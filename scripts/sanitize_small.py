@@ -1,0 +1,42 @@
+"""Small invocations of every kernel family, for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import item_alignment_b200 as ia
+from item_alignment_b200 import functional as F_
+dev = torch.device("cuda:0")
+g = torch.Generator(device=dev).manual_seed(0)
+for dt, n, d in ((torch.bfloat16, 300, 1024), (torch.float32, 257, 768), (torch.float32, 33, 50), (torch.float16, 64, 2048)):
+    x = torch.tanh(torch.randn(n, d, device=dev, generator=g)).to(dt); y = torch.tanh(torch.randn(n, d, device=dev, generator=g)).to(dt)
+    l = (torch.rand(n, device=dev, generator=g) < 0.5).long()
+    for m in ("inner_product", "cosine", "l1", "l2"):
+        F_.pair_score_raw(m, x, y, threshold=0.5)
+        F_.pair_score_loss_raw(m, "hinge", x, y, l)
+        F_.pair_score_loss_raw(m, "cosine", x, y, l, grad_dtype=torch.float32)
+        gs = torch.randn(n, device=dev); F_.pair_score_bwd_raw(m, x, y, gs)
+    if d % 8 == 0:
+        w = torch.randn(2, 2 * d, device=dev) * 0.02; b = torch.zeros(2, device=dev)
+        F_.softmax_head_raw(x, y, w, b, l); F_.softmax_head_raw(x, y, w, b)
+os.environ.pop("IA_PAIR_BULK", None)
+n, d = 20000, 1024
+x = torch.tanh(torch.randn(n, d, device=dev, generator=g)).to(torch.bfloat16); y = torch.tanh(torch.randn(n, d, device=dev, generator=g)).to(torch.bfloat16)
+l = (torch.rand(n, device=dev, generator=g) < 0.5).long()
+F_.pair_score_loss_raw("inner_product", "bce", x, y, l)        # ROWS=2 path
+w = torch.randn(2, 2 * d, device=dev) * 0.02; b = torch.zeros(2, device=dev)
+F_.softmax_head_raw(x, y, w, b, l)                             # grouped ring path
+cat = torch.tanh(torch.randn(3000, 128, device=dev, generator=g)).to(torch.bfloat16)
+q = torch.tanh(torch.randn(130, 128, device=dev, generator=g)).to(torch.bfloat16)
+with ia.CatalogIndex(cat) as idx:
+    for k in (100, 10, 1):
+        for m in ("cosine", "inner_product", "l1", "l2"):
+            idx.topk(q, k, m)
+    keys = idx.topk_keys(q, 10, "cosine")
+    bound = (keys[:, 9] >> 32) & 0xFFFFFFFF
+    idx.topk_keys(q, 100, "cosine", init_tau=bound)
+with ia.CatalogIndex(cat.float()) as idx:
+    idx.topk(q.float(), 20, "cosine")
+ia.merge_keys(torch.stack([keys, keys]), 10)
+emb = cat; F_.pair_score_gather_raw("cosine", emb, emb, torch.arange(100, device=dev), torch.arange(100, 200, device=dev))
+ia.threshold_sweep(torch.rand(5000, device=dev), (torch.rand(5000, device=dev) < 0.5).long())
+torch.cuda.synchronize()
+print("sanitize_small: done")
