@@ -49,11 +49,13 @@ __device__ __forceinline__ int swz(int e) {
 
 constexpr int kHeadMaxStages = 4;   // rows in flight per warp in the bulk-copy ring (TRAIN kernel), fewer if smem is short
 
-// TRAIN keeps 2*VPL*E dW accumulators per lane in registers, which limits it to one CTA (8 warps) per SM: the
-// rows therefore arrive through a per-warp shared-memory ring filled by cp.async.bulk (p.stages rows in flight
-// per warp regardless of registers).  The forward-only kernel is light and uses plain streaming loads.
-template <typename T, typename G, bool TRAIN, int VPL>
-__global__ void __launch_bounds__(256) softmax_head_kernel(const HeadParams p) {
+// TRAIN keeps 2*VPL*E dW accumulators per lane in registers.  To still have enough warps to hide latency it runs
+// NW = 16 warps per CTA (one CTA per SM, <= 128 registers per thread) whenever the row ring fits, and the rows
+// arrive through a per-warp shared-memory ring filled by cp.async.bulk (p.stages rows in flight per warp regardless
+// of registers); x and y are read from the ring twice (logits, then gradients) instead of being held in registers.
+// The forward-only kernel is light: 8 warps, plain streaming loads.
+template <typename T, typename G, bool TRAIN, int VPL, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) softmax_head_kernel(const HeadParams p) {
   constexpr int E = VecTraits<T>::kElems;
   constexpr int C = E / 4;            // float4 chunks per 128-bit input vector
   constexpr int P4 = VPL * 32 * C;    // float4 per (padded) weight-row half
@@ -77,32 +79,26 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const HeadParams p) {
     if (TRAIN) { sw[16 * P4 + pos] = c - a; sacc[i] = 0.f; }
   }
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t warps_total = (int64_t)gridDim.x * 8;
+  const int64_t warps_total = (int64_t)gridDim.x * NW;
   const int nvec = h / E;
   const uint32_t row_bytes = (uint32_t)h * (uint32_t)sizeof(T);
   uint8_t* ring_base = reinterpret_cast<uint8_t*>(sacc + ((h2 + 3) & ~3));
-  const int R = p.group;                                  // adjacent pairs per stage
-  const size_t stage_bytes = (size_t)R * 2 * row_bytes;   // [x rows | y rows]
+  const size_t stage_bytes = (size_t)2 * row_bytes;        // [x row | y row]
   uint8_t* ring = ring_base + (size_t)wib * p.stages * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_base + (size_t)8 * p.stages * stage_bytes) + wib * p.stages;
-  const int64_t row0 = (int64_t)blockIdx.x * 8 + wib;     // index of the warp's first row GROUP
-  const int64_t n_groups = (p.n + R - 1) / R;
-  auto arm = [&](int stage, int64_t grp) {   // lane 0 only
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_base + (size_t)NW * p.stages * stage_bytes) + wib * p.stages;
+  const int64_t row0 = (int64_t)blockIdx.x * NW + wib;
+  auto arm = [&](int stage, int64_t row) {   // lane 0 only
     uint8_t* dst = ring + (size_t)stage * stage_bytes;
-    const int64_t r0 = grp * R;
-    const int live = (int)((p.n - r0) < R ? (p.n - r0) : R);
-    mbar_arrive_expect_tx(&bars[stage], (uint32_t)(live * 2 * row_bytes));
-    for (int k = 0; k < live; ++k) {
-      bulk_load_1d(dst + (size_t)k * row_bytes, static_cast<const T*>(p.x) + (r0 + k) * p.ldx, row_bytes, &bars[stage]);
-      bulk_load_1d(dst + (size_t)(R + k) * row_bytes, static_cast<const T*>(p.y) + (r0 + k) * p.ldy, row_bytes, &bars[stage]);
-    }
+    mbar_arrive_expect_tx(&bars[stage], 2 * row_bytes);
+    bulk_load_1d(dst, static_cast<const T*>(p.x) + row * p.ldx, row_bytes, &bars[stage]);
+    bulk_load_1d(dst + row_bytes, static_cast<const T*>(p.y) + row * p.ldy, row_bytes, &bars[stage]);
   };
   if (TRAIN) {
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) mbar_init(&bars[s], 1);
       fence_mbar_init();
       for (int s = 0; s < p.stages; ++s)
-        if (row0 + s * warps_total < n_groups) arm(s, row0 + s * warps_total);
+        if (row0 + s * warps_total < p.n) arm(s, row0 + s * warps_total);
     }
   }
   __syncthreads();
@@ -116,33 +112,16 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const HeadParams p) {
   float loss_acc = 0.f, db_acc = 0.f;
 
   int it = 0;
-  const int64_t n_iter_items = TRAIN ? n_groups : p.n;
-  for (int64_t item = row0; item < n_iter_items; item += warps_total, ++it) {
-   const int stage = TRAIN ? it % p.stages : 0;
-   if (TRAIN) mbar_wait(&bars[stage], (uint32_t)(it / p.stages) & 1u);
-   const int live_rows = TRAIN ? (int)((p.n - item * R) < R ? (p.n - item * R) : R) : 1;
-   for (int k = 0; k < live_rows; ++k) {
-    const int64_t row = TRAIN ? item * R + k : item;
-    uint4 xv[VPL], yv[VPL];
+  for (int64_t row = row0; row < p.n; row += warps_total, ++it) {
+    const int stage = TRAIN ? it % p.stages : 0;
+    const uint4* xs = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_bytes);
+    const uint4* ys = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_bytes + row_bytes);
+    const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + row * p.ldx);
+    const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + row * p.ldy);
+    uint4 xv[TRAIN ? 1 : VPL], yv[TRAIN ? 1 : VPL];
     if (TRAIN) {
-      const uint4* xs = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_bytes + (size_t)k * row_bytes);
-      const uint4* ys = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_bytes + (size_t)(R + k) * row_bytes);
-#pragma unroll
-      for (int i = 0; i < VPL; ++i) {
-        const int v = lane + 32 * i;
-        if (v < nvec) { xv[i] = xs[v]; yv[i] = ys[v]; }
-        else { xv[i] = make_uint4(0, 0, 0, 0); yv[i] = make_uint4(0, 0, 0, 0); }
-      }
-      if (k == live_rows - 1) {          // the whole stage is in registers / consumed: refill it
-        __syncwarp();
-        if (lane == 0) {
-          const int64_t next = item + (int64_t)p.stages * warps_total;
-          if (next < n_groups) { fence_proxy_async(); arm(stage, next); }
-        }
-      }
+      mbar_wait(&bars[stage], (uint32_t)(it / p.stages) & 1u);
     } else {
-      const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + row * p.ldx);
-      const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + row * p.ldy);
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
         const int v = lane + 32 * i;
@@ -155,10 +134,11 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const HeadParams p) {
     float l0x = 0.f, l0y = 0.f, l1x = 0.f, l1y = 0.f;     // four independent FMA chains
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      if (lane + 32 * i < nvec) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
         float fx[E], fy[E];
-        unpack<T>(xv[i], fx);
-        unpack<T>(yv[i], fy);
+        unpack<T>(TRAIN ? xs[v] : xv[TRAIN ? 0 : i], fx);
+        unpack<T>(TRAIN ? ys[v] : yv[TRAIN ? 0 : i], fy);
 #pragma unroll
         for (int q = 0; q < C; ++q) {
           const int f4 = (i * C + q) * 32 + lane;
@@ -195,8 +175,8 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const HeadParams p) {
       const int v = lane + 32 * i;
       if (v < nvec) {
         float fx[E], fy[E], gx[E], gy[E];
-        unpack<T>(xv[i], fx);
-        unpack<T>(yv[i], fy);
+        unpack<T>(xs[v], fx);
+        unpack<T>(ys[v], fy);
 #pragma unroll
         for (int q = 0; q < C; ++q) {
           const int f4 = (i * C + q) * 32 + lane;
@@ -215,12 +195,17 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const HeadParams p) {
         }
       }
     }
-   }   // rows of the stage
+    // the row has been consumed from the ring: refill its slot
+    __syncwarp();
+    if (lane == 0) {
+      const int64_t next = row + (int64_t)p.stages * warps_total;
+      if (next < p.n) { fence_proxy_async(); arm(stage, next); }
+    }
   }
 
   if (TRAIN) {
     // fixed-order block reduction of the per-lane dW accumulators: warp 0, then warp 1, ...
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < NW; ++w) {
       if (wib == w) {
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
@@ -236,7 +221,7 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const HeadParams p) {
       }
       __syncthreads();
     }
-    __shared__ float wl[8], wdb[8];
+    __shared__ float wl[NW], wdb[NW];
     if (lane == 0) { wl[wib] = loss_acc; wdb[wib] = db_acc; }
     __syncthreads();
     float* part = reinterpret_cast<float*>(static_cast<char*>(p.workspace) + kWorkspaceBytes) +
@@ -245,7 +230,7 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const HeadParams p) {
     double blk = 0.0;
     if (threadIdx.x == 0) {
       float dbs = 0.f;
-      for (int w = 0; w < 8; ++w) { blk += (double)wl[w]; dbs += wdb[w]; }
+      for (int w = 0; w < NW; ++w) { blk += (double)wl[w]; dbs += wdb[w]; }
       part[h2] = dbs;
     }
     grid_sum_finish(blk, p.workspace, p.loss_out, p.loss_scale);
@@ -266,35 +251,22 @@ __global__ void __launch_bounds__(256) softmax_head_finalize(const float* partia
   }
 }
 
-template <typename T, typename G, bool TRAIN, int VPL>
-static int launch_head_one(const HeadParams& p_in, cudaStream_t stream, float* dw, float* db) {
-  auto kernel = softmax_head_kernel<T, G, TRAIN, VPL>;
-  constexpr int P4 = VPL * 32 * (VecTraits<T>::kElems / 4);
-  const size_t w_bytes = (size_t)(TRAIN ? 6 : 4) * P4 * 16;
+template <typename T, typename G, bool TRAIN, int VPL, int NW>
+static int launch_head_nw(const HeadParams& p_in, int stages, size_t smem, cudaStream_t stream, float* dw, float* db) {
+  auto kernel = softmax_head_kernel<T, G, TRAIN, VPL, NW>;
   HeadParams p = p_in;
-  const size_t fixed = w_bytes + (size_t)(((2 * p.h + 3) & ~3)) * 4;
-  const size_t row_bytes = (size_t)p.h * sizeof(T);
-  p.group = (row_bytes >= 1536 && row_bytes <= 3072 && p.n >= 16384) ? 2 : 1;   // 4-6 KB chunks stream best (see pair kernel)
-  const size_t per_stage = (size_t)8 * p.group * 2 * row_bytes + 8 * 8;
-  int stages = kHeadMaxStages;
-  while (stages > 1 && fixed + stages * per_stage > 227 * 1024) --stages;
   p.stages = stages;
-  const size_t smem = TRAIN ? fixed + stages * per_stage : w_bytes;
-  if (smem > 227 * 1024) { set_error("h too large for the shared-memory W tile + row ring"); return IA_ERR_UNSUPPORTED; }
-  static bool configured = false;
-  static int bps = 0;
+  p.group = 1;
   static size_t configured_smem = 0;
-  if (!configured || smem > configured_smem) {
+  if (smem > configured_smem) {
     IA_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bps = blocks_per_sm(kernel, 256, smem);
-    configured = true;
     configured_smem = smem;
   }
-  int64_t want = (p.n / (TRAIN ? p.group : 1) + 7) / 8;
-  int64_t cap = (int64_t)sm_count() * bps;
+  int64_t want = (p.n + NW - 1) / NW;
+  int64_t cap = (int64_t)sm_count() * (TRAIN ? 1 : blocks_per_sm(kernel, NW * 32, smem));
   if (cap > kHeadMaxGrid) cap = kHeadMaxGrid;
   const int grid = (int)(want < cap ? want : cap);
-  kernel<<<grid, 256, smem, stream>>>(p);
+  kernel<<<grid, NW * 32, smem, stream>>>(p);
   IA_LAUNCH_CHECK();
   if (TRAIN && (dw || db)) {
     const float* partials = reinterpret_cast<const float*>(static_cast<const char*>(p.workspace) + kWorkspaceBytes);
@@ -303,6 +275,26 @@ static int launch_head_one(const HeadParams& p_in, cudaStream_t stream, float* d
     IA_LAUNCH_CHECK();
   }
   return IA_OK;
+}
+
+template <typename T, typename G, bool TRAIN, int VPL>
+static int launch_head_one(const HeadParams& p, cudaStream_t stream, float* dw, float* db) {
+  constexpr int P4 = VPL * 32 * (VecTraits<T>::kElems / 4);
+  const size_t w_bytes = (size_t)(TRAIN ? 6 : 4) * P4 * 16;
+  if (!TRAIN) return launch_head_nw<T, G, false, VPL, 8>(p, 1, w_bytes, stream, dw, db);
+  const size_t fixed = w_bytes + (size_t)(((2 * p.h + 3) & ~3)) * 4;
+  const size_t row_bytes = (size_t)p.h * sizeof(T);
+  auto fit = [&](int nw) {   // deepest ring (>= 2 stages) that fits next to the W tiles
+    int st = kHeadMaxStages;
+    while (st > 1 && fixed + (size_t)nw * st * (2 * row_bytes + 8) > 227 * 1024) --st;
+    return st;
+  };
+  const int st16 = fit(16), st8 = fit(8);
+  if (st16 >= 2) return launch_head_nw<T, G, true, VPL, 16>(p, st16, fixed + (size_t)16 * st16 * (2 * row_bytes + 8), stream, dw, db);
+  if (st8 >= 2 || fixed + (size_t)8 * (2 * row_bytes + 8) <= 227 * 1024)
+    return launch_head_nw<T, G, true, VPL, 8>(p, st8, fixed + (size_t)8 * st8 * (2 * row_bytes + 8), stream, dw, db);
+  set_error("h too large for the shared-memory W tile + row ring");
+  return IA_ERR_UNSUPPORTED;
 }
 
 template <typename T, typename G>
