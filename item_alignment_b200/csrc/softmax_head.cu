@@ -51,8 +51,9 @@ constexpr int kHeadMaxStages = 4;   // rows in flight per warp in the bulk-copy 
 
 // TRAIN keeps 2*VPL*E dW accumulators per lane in registers.  To still have enough warps to hide latency it runs
 // NW = 16 warps per CTA (one CTA per SM, <= 128 registers per thread) whenever the row ring fits, and the rows
-// arrive through a per-warp shared-memory ring filled by cp.async.bulk (p.stages rows in flight per warp regardless
+// arrive through a per-warp shared-memory ring filled with cp.async (p.stages rows in flight per warp regardless
 // of registers); x and y are read from the ring twice (logits, then gradients) instead of being held in registers.
+// (A cp.async.bulk ring was measured first: at 2 KB per copy the TMA unit's per-operation cost capped it at 55 %.)
 // The forward-only kernel is light: 8 warps, plain streaming loads.
 template <typename T, typename G, bool TRAIN, int VPL, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) softmax_head_kernel(const HeadParams p) {
@@ -85,21 +86,27 @@ __global__ void __launch_bounds__(NW * 32, 1) softmax_head_kernel(const HeadPara
   uint8_t* ring_base = reinterpret_cast<uint8_t*>(sacc + ((h2 + 3) & ~3));
   const size_t stage_bytes = (size_t)2 * row_bytes;        // [x row | y row]
   uint8_t* ring = ring_base + (size_t)wib * p.stages * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_base + (size_t)NW * p.stages * stage_bytes) + wib * p.stages;
   const int64_t row0 = (int64_t)blockIdx.x * NW + wib;
-  auto arm = [&](int stage, int64_t row) {   // lane 0 only
-    uint8_t* dst = ring + (size_t)stage * stage_bytes;
-    mbar_arrive_expect_tx(&bars[stage], 2 * row_bytes);
-    bulk_load_1d(dst, static_cast<const T*>(p.x) + row * p.ldx, row_bytes, &bars[stage]);
-    bulk_load_1d(dst + row_bytes, static_cast<const T*>(p.y) + row * p.ldy, row_bytes, &bars[stage]);
+  // every lane copies (cp.async, 16 B each, L2 -> shared without registers) exactly the vectors it will consume, so
+  // the ring needs no cross-lane synchronisation: commit one group per row, wait_group(stages-1) before reading
+  auto arm = [&](int stage, int64_t row) {
+    if (row < p.n) {
+      const uint32_t dst = smem_u32(ring + (size_t)stage * stage_bytes);
+      const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + row * p.ldx);
+      const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + row * p.ldy);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)v * 16u), "l"(xr + v) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + row_bytes + (uint32_t)v * 16u), "l"(yr + v) : "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");   // always commit: group counting stays uniform
   };
   if (TRAIN) {
-    if (lane == 0) {
-      for (int s = 0; s < p.stages; ++s) mbar_init(&bars[s], 1);
-      fence_mbar_init();
-      for (int s = 0; s < p.stages; ++s)
-        if (row0 + s * warps_total < p.n) arm(s, row0 + s * warps_total);
-    }
+    for (int s = 0; s < p.stages; ++s) arm(s, row0 + s * warps_total);
   }
   __syncthreads();
   const float b0 = p.b[0], b1 = p.b[1];
@@ -120,7 +127,11 @@ __global__ void __launch_bounds__(NW * 32, 1) softmax_head_kernel(const HeadPara
     const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + row * p.ldy);
     uint4 xv[TRAIN ? 1 : VPL], yv[TRAIN ? 1 : VPL];
     if (TRAIN) {
-      mbar_wait(&bars[stage], (uint32_t)(it / p.stages) & 1u);
+      // the oldest outstanding group is this row's
+      if (p.stages == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
+      else if (p.stages == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+      else if (p.stages == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else {
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
@@ -195,12 +206,8 @@ __global__ void __launch_bounds__(NW * 32, 1) softmax_head_kernel(const HeadPara
         }
       }
     }
-    // the row has been consumed from the ring: refill its slot
-    __syncwarp();
-    if (lane == 0) {
-      const int64_t next = row + (int64_t)p.stages * warps_total;
-      if (next < p.n) { fence_proxy_async(); arm(stage, next); }
-    }
+    // the row has been consumed from the ring: refill its slot (same lane wrote and read it: no sync needed)
+    arm(stage, row + (int64_t)p.stages * warps_total);
   }
 
   if (TRAIN) {
