@@ -49,19 +49,21 @@ __device__ __forceinline__ int swz(int e) {
 
 constexpr int kHeadMaxStages = 4;   // rows in flight per warp in the bulk-copy ring (TRAIN kernel), fewer if smem is short
 
-// TRAIN keeps 2*VPL*E dW accumulators per lane in registers.  To still have enough warps to hide latency it runs
-// NW = 16 warps per CTA (one CTA per SM, <= 128 registers per thread) whenever the row ring fits, and the rows
-// arrive through a per-warp shared-memory ring filled with cp.async (p.stages rows in flight per warp regardless
-// of registers); x and y are read from the ring twice (logits, then gradients) instead of being held in registers.
-// (A cp.async.bulk ring was measured first: at 2 KB per copy the TMA unit's per-operation cost capped it at 55 %.)
-// The forward-only kernel is light: 8 warps, plain streaming loads.
-template <typename T, typename G, bool TRAIN, int VPL, int NW>
-__global__ void __launch_bounds__(NW * 32, 1) softmax_head_kernel(const HeadParams p) {
+// The training kernel is bound by SHARED-MEMORY bandwidth if every row re-reads the whole W tile (6 float4 arrays,
+// 24 KB per row per warp at h = 1024): it therefore processes RR rows per iteration -- each W chunk is loaded once and
+// applied to RR rows held in registers -- and keeps 2*VPL*E dW accumulators per lane.  With that many registers only
+// 8 warps fit per SM, so the rows arrive through a per-warp shared-memory ring filled with cp.async (every lane copies
+// exactly the vectors it will consume: no cross-lane synchronisation), p.stages row groups in flight per warp.
+// (Measured first: a cp.async.bulk ring and a 16-warp variant both sat at 55 % -- the W re-reads were the limit.)
+// The forward-only kernel is light: plain streaming loads, RR = 1.
+template <typename T, typename G, bool TRAIN, int VPL, int RR>
+__global__ void __launch_bounds__(256, 1) softmax_head_kernel(const HeadParams p) {
+  constexpr int NW = 8;
   constexpr int E = VecTraits<T>::kElems;
   constexpr int C = E / 4;            // float4 chunks per 128-bit input vector
   constexpr int P4 = VPL * 32 * C;    // float4 per (padded) weight-row half
   extern __shared__ float4 smem4[];
-  // [w0x | w0y | w1x | w1y | (TRAIN) wdx | wdy | sacc[2h] | ring | barriers]
+  // [w0x | w0y | w1x | w1y | (TRAIN) wdx | wdy | sacc[2h] | ring]
   const float4* w0x = smem4;
   const float4* w0y = smem4 + P4;
   const float4* w1x = smem4 + 2 * P4;
@@ -84,29 +86,34 @@ __global__ void __launch_bounds__(NW * 32, 1) softmax_head_kernel(const HeadPara
   const int nvec = h / E;
   const uint32_t row_bytes = (uint32_t)h * (uint32_t)sizeof(T);
   uint8_t* ring_base = reinterpret_cast<uint8_t*>(sacc + ((h2 + 3) & ~3));
-  const size_t stage_bytes = (size_t)2 * row_bytes;        // [x row | y row]
+  const size_t stage_bytes = (size_t)RR * 2 * row_bytes;   // RR x [x row | y row]
   uint8_t* ring = ring_base + (size_t)wib * p.stages * stage_bytes;
-  const int64_t row0 = (int64_t)blockIdx.x * NW + wib;
-  // every lane copies (cp.async, 16 B each, L2 -> shared without registers) exactly the vectors it will consume, so
-  // the ring needs no cross-lane synchronisation: commit one group per row, wait_group(stages-1) before reading
-  auto arm = [&](int stage, int64_t row) {
-    if (row < p.n) {
-      const uint32_t dst = smem_u32(ring + (size_t)stage * stage_bytes);
-      const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + row * p.ldx);
-      const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + row * p.ldy);
+  const int64_t n_groups = (p.n + RR - 1) / RR;           // a warp owns RR adjacent rows per iteration
+  const int64_t grp0 = (int64_t)blockIdx.x * NW + wib;
+  auto arm = [&](int stage, int64_t grp) {
+    if (grp < n_groups) {
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) {
-        const int v = lane + 32 * i;
-        if (v < nvec) {
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)v * 16u), "l"(xr + v) : "memory");
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + row_bytes + (uint32_t)v * 16u), "l"(yr + v) : "memory");
+      for (int k = 0; k < RR; ++k) {
+        const int64_t row = grp * RR + k;
+        if (row < p.n) {
+          const uint32_t dst = smem_u32(ring + (size_t)stage * stage_bytes + (size_t)k * 2 * row_bytes);
+          const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + row * p.ldx);
+          const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + row * p.ldy);
+#pragma unroll
+          for (int i = 0; i < VPL; ++i) {
+            const int v = lane + 32 * i;
+            if (v < nvec) {
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)v * 16u), "l"(xr + v) : "memory");
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + row_bytes + (uint32_t)v * 16u), "l"(yr + v) : "memory");
+            }
+          }
         }
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");   // always commit: group counting stays uniform
   };
   if (TRAIN) {
-    for (int s = 0; s < p.stages; ++s) arm(s, row0 + s * warps_total);
+    for (int s = 0; s < p.stages; ++s) arm(s, grp0 + s * warps_total);
   }
   __syncthreads();
   const float b0 = p.b[0], b1 = p.b[1];
@@ -119,98 +126,127 @@ __global__ void __launch_bounds__(NW * 32, 1) softmax_head_kernel(const HeadPara
   float loss_acc = 0.f, db_acc = 0.f;
 
   int it = 0;
-  for (int64_t row = row0; row < p.n; row += warps_total, ++it) {
+  for (int64_t grp = grp0; grp < n_groups; grp += warps_total, ++it) {
     const int stage = TRAIN ? it % p.stages : 0;
-    const uint4* xs = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_bytes);
-    const uint4* ys = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_bytes + row_bytes);
-    const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + row * p.ldx);
-    const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + row * p.ldy);
-    uint4 xv[TRAIN ? 1 : VPL], yv[TRAIN ? 1 : VPL];
+    uint4 xv[RR][VPL], yv[RR][VPL];
+    bool live[RR];
+    int64_t rows[RR];
+#pragma unroll
+    for (int k = 0; k < RR; ++k) { rows[k] = grp * RR + k; live[k] = rows[k] < p.n; }
     if (TRAIN) {
-      // the oldest outstanding group is this row's
       if (p.stages == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
       else if (p.stages == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
       else if (p.stages == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
       else asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+      for (int k = 0; k < RR; ++k) {
+        const uint4* xs = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_bytes + (size_t)k * 2 * row_bytes);
+        const uint4* ys = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_bytes + (size_t)k * 2 * row_bytes + row_bytes);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const int v = lane + 32 * i;
+          if (live[k] && v < nvec) { xv[k][i] = xs[v]; yv[k][i] = ys[v]; }
+          else { xv[k][i] = make_uint4(0, 0, 0, 0); yv[k][i] = make_uint4(0, 0, 0, 0); }
+        }
+      }
+      arm(stage, grp + (int64_t)p.stages * warps_total);   // the slot is in registers now: refill it
     } else {
+      const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + rows[0] * p.ldx);
+      const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + rows[0] * p.ldy);
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
         const int v = lane + 32 * i;
-        if (v < nvec) { xv[i] = ldg_stream(xr + v); yv[i] = ldg_stream(yr + v); }
-        else { xv[i] = make_uint4(0, 0, 0, 0); yv[i] = make_uint4(0, 0, 0, 0); }
+        if (v < nvec) { xv[0][i] = ldg_stream(xr + v); yv[0][i] = ldg_stream(yr + v); }
+        else { xv[0][i] = make_uint4(0, 0, 0, 0); yv[0][i] = make_uint4(0, 0, 0, 0); }
       }
     }
-    int label = 0;
-    if (TRAIN) label = (int)(__ldg(p.labels + row) != 0);
-    float l0x = 0.f, l0y = 0.f, l1x = 0.f, l1y = 0.f;     // four independent FMA chains
+    // ---- logits: every W chunk is read once and applied to all RR rows
+    float l0[RR], l1[RR], l0b[RR], l1b[RR];
+#pragma unroll
+    for (int k = 0; k < RR; ++k) { l0[k] = 0.f; l1[k] = 0.f; l0b[k] = 0.f; l1b[k] = 0.f; }
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nvec) {
-        float fx[E], fy[E];
-        unpack<T>(TRAIN ? xs[v] : xv[TRAIN ? 0 : i], fx);
-        unpack<T>(TRAIN ? ys[v] : yv[TRAIN ? 0 : i], fy);
+      if (lane + 32 * i < nvec) {
 #pragma unroll
         for (int q = 0; q < C; ++q) {
           const int f4 = (i * C + q) * 32 + lane;
           const float4 a0 = w0x[f4], a1 = w0y[f4], c0 = w1x[f4], c1 = w1y[f4];
-          l0x = fmaf(fx[4 * q + 0], a0.x, l0x); l0x = fmaf(fx[4 * q + 1], a0.y, l0x);
-          l0x = fmaf(fx[4 * q + 2], a0.z, l0x); l0x = fmaf(fx[4 * q + 3], a0.w, l0x);
-          l0y = fmaf(fy[4 * q + 0], a1.x, l0y); l0y = fmaf(fy[4 * q + 1], a1.y, l0y);
-          l0y = fmaf(fy[4 * q + 2], a1.z, l0y); l0y = fmaf(fy[4 * q + 3], a1.w, l0y);
-          l1x = fmaf(fx[4 * q + 0], c0.x, l1x); l1x = fmaf(fx[4 * q + 1], c0.y, l1x);
-          l1x = fmaf(fx[4 * q + 2], c0.z, l1x); l1x = fmaf(fx[4 * q + 3], c0.w, l1x);
-          l1y = fmaf(fy[4 * q + 0], c1.x, l1y); l1y = fmaf(fy[4 * q + 1], c1.y, l1y);
-          l1y = fmaf(fy[4 * q + 2], c1.z, l1y); l1y = fmaf(fy[4 * q + 3], c1.w, l1y);
+#pragma unroll
+          for (int k = 0; k < RR; ++k) {
+            float fx[E], fy[E];
+            unpack<T>(xv[k][i], fx);
+            unpack<T>(yv[k][i], fy);
+            l0[k] = fmaf(fx[4 * q + 0], a0.x, l0[k]); l0[k] = fmaf(fx[4 * q + 1], a0.y, l0[k]);
+            l0[k] = fmaf(fx[4 * q + 2], a0.z, l0[k]); l0[k] = fmaf(fx[4 * q + 3], a0.w, l0[k]);
+            l0b[k] = fmaf(fy[4 * q + 0], a1.x, l0b[k]); l0b[k] = fmaf(fy[4 * q + 1], a1.y, l0b[k]);
+            l0b[k] = fmaf(fy[4 * q + 2], a1.z, l0b[k]); l0b[k] = fmaf(fy[4 * q + 3], a1.w, l0b[k]);
+            l1[k] = fmaf(fx[4 * q + 0], c0.x, l1[k]); l1[k] = fmaf(fx[4 * q + 1], c0.y, l1[k]);
+            l1[k] = fmaf(fx[4 * q + 2], c0.z, l1[k]); l1[k] = fmaf(fx[4 * q + 3], c0.w, l1[k]);
+            l1b[k] = fmaf(fy[4 * q + 0], c1.x, l1b[k]); l1b[k] = fmaf(fy[4 * q + 1], c1.y, l1b[k]);
+            l1b[k] = fmaf(fy[4 * q + 2], c1.z, l1b[k]); l1b[k] = fmaf(fy[4 * q + 3], c1.w, l1b[k]);
+          }
         }
       }
     }
-    const float l0 = warp_sum(l0x + l0y) + b0;
-    const float l1 = warp_sum(l1x + l1y) + b1;
-    const float m = fmaxf(l0, l1);
-    const float e0 = expf(l0 - m), e1 = expf(l1 - m);
-    const float den = e0 + e1;
-    const float p0 = e0 / den, p1 = e1 / den;
-    if (lane == 0) {
-      if (p.logits) { p.logits[2 * row] = l0; p.logits[2 * row + 1] = l1; }
-      if (p.probs) { p.probs[2 * row] = p0; p.probs[2 * row + 1] = p1; }
+    float delta[RR];
+#pragma unroll
+    for (int k = 0; k < RR; ++k) {
+      const float z0 = warp_sum(l0[k] + l0b[k]) + b0;
+      const float z1 = warp_sum(l1[k] + l1b[k]) + b1;
+      const float m = fmaxf(z0, z1);
+      const float e0 = expf(z0 - m), e1 = expf(z1 - m);
+      const float den = e0 + e1;
+      const float p0 = e0 / den, p1 = e1 / den;
+      delta[k] = 0.f;
+      if (live[k]) {
+        if (lane == 0) {
+          if (p.logits) { p.logits[2 * rows[k]] = z0; p.logits[2 * rows[k] + 1] = z1; }
+          if (p.probs) { p.probs[2 * rows[k]] = p0; p.probs[2 * rows[k] + 1] = p1; }
+        }
+        if (TRAIN) {
+          const int label = (int)(__ldg(p.labels + rows[k]) != 0);
+          loss_acc += logf(den) - ((label ? z1 : z0) - m);         // -log softmax[label]
+          delta[k] = (label ? -p0 : p1) * p.grad_scale;             // d loss / d logit1 ( = -d loss / d logit0 )
+          db_acc += delta[k];
+        }
+      }
     }
     if (!TRAIN) continue;
-    loss_acc += logf(den) - ((label ? l1 : l0) - m);   // -log softmax[label]
-    const float delta = (label ? -p0 : p1) * p.grad_scale;   // d loss / d logit1 ( = -d loss / d logit0 )
-    db_acc += delta;
-    G* dxr = p.dx ? static_cast<G*>(p.dx) + row * p.lddx : nullptr;
-    G* dyr = p.dx ? static_cast<G*>(p.dy) + row * p.lddy : nullptr;
+    // ---- gradients: dx = delta * (W1x - W0x), dW accumulators += delta * x; again one W read for RR rows
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int v = lane + 32 * i;
       if (v < nvec) {
-        float fx[E], fy[E], gx[E], gy[E];
-        unpack<T>(xs[v], fx);
-        unpack<T>(ys[v], fy);
+        float4 d0[C], d1[C];
 #pragma unroll
-        for (int q = 0; q < C; ++q) {
-          const int f4 = (i * C + q) * 32 + lane;
-          const float4 d0 = wdx[f4], d1 = wdy[f4];
-          gx[4 * q + 0] = delta * d0.x; gx[4 * q + 1] = delta * d0.y; gx[4 * q + 2] = delta * d0.z; gx[4 * q + 3] = delta * d0.w;
-          gy[4 * q + 0] = delta * d1.x; gy[4 * q + 1] = delta * d1.y; gy[4 * q + 2] = delta * d1.z; gy[4 * q + 3] = delta * d1.w;
-        }
+        for (int q = 0; q < C; ++q) { d0[q] = wdx[(i * C + q) * 32 + lane]; d1[q] = wdy[(i * C + q) * 32 + lane]; }
 #pragma unroll
-        for (int j = 0; j < E; ++j) {
-          accx[i * E + j] = fmaf(delta, fx[j], accx[i * E + j]);
-          accy[i * E + j] = fmaf(delta, fy[j], accy[i * E + j]);
-        }
-        if (dxr) {
-          Packer<G, E>::store(dxr + (int64_t)v * E, gx);
-          Packer<G, E>::store(dyr + (int64_t)v * E, gy);
+        for (int k = 0; k < RR; ++k) {
+          if (!live[k]) continue;
+          float fx[E], fy[E], gx[E], gy[E];
+          unpack<T>(xv[k][i], fx);
+          unpack<T>(yv[k][i], fy);
+#pragma unroll
+          for (int q = 0; q < C; ++q) {
+            gx[4 * q + 0] = delta[k] * d0[q].x; gx[4 * q + 1] = delta[k] * d0[q].y; gx[4 * q + 2] = delta[k] * d0[q].z; gx[4 * q + 3] = delta[k] * d0[q].w;
+            gy[4 * q + 0] = delta[k] * d1[q].x; gy[4 * q + 1] = delta[k] * d1[q].y; gy[4 * q + 2] = delta[k] * d1[q].z; gy[4 * q + 3] = delta[k] * d1[q].w;
+          }
+#pragma unroll
+          for (int j = 0; j < E; ++j) {
+            accx[i * E + j] = fmaf(delta[k], fx[j], accx[i * E + j]);
+            accy[i * E + j] = fmaf(delta[k], fy[j], accy[i * E + j]);
+          }
+          if (p.dx) {
+            Packer<G, E>::store(static_cast<G*>(p.dx) + rows[k] * p.lddx + (int64_t)v * E, gx);
+            Packer<G, E>::store(static_cast<G*>(p.dy) + rows[k] * p.lddy + (int64_t)v * E, gy);
+          }
         }
       }
     }
-    // the row has been consumed from the ring: refill its slot (same lane wrote and read it: no sync needed)
-    arm(stage, row + (int64_t)p.stages * warps_total);
   }
 
   if (TRAIN) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     // fixed-order block reduction of the per-lane dW accumulators: warp 0, then warp 1, ...
     for (int w = 0; w < NW; ++w) {
       if (wib == w) {
@@ -258,22 +294,23 @@ __global__ void __launch_bounds__(256) softmax_head_finalize(const float* partia
   }
 }
 
-template <typename T, typename G, bool TRAIN, int VPL, int NW>
-static int launch_head_nw(const HeadParams& p_in, int stages, size_t smem, cudaStream_t stream, float* dw, float* db) {
-  auto kernel = softmax_head_kernel<T, G, TRAIN, VPL, NW>;
+template <typename T, typename G, bool TRAIN, int VPL, int RR>
+static int launch_head_rr(const HeadParams& p_in, int stages, size_t smem, cudaStream_t stream, float* dw, float* db) {
+  auto kernel = softmax_head_kernel<T, G, TRAIN, VPL, RR>;
   HeadParams p = p_in;
   p.stages = stages;
-  p.group = 1;
+  p.group = RR;
   static size_t configured_smem = 0;
   if (smem > configured_smem) {
     IA_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured_smem = smem;
   }
-  int64_t want = (p.n + NW - 1) / NW;
-  int64_t cap = (int64_t)sm_count() * (TRAIN ? 1 : blocks_per_sm(kernel, NW * 32, smem));
+  const int64_t groups = (p.n + RR - 1) / RR;
+  int64_t want = (groups + 7) / 8;
+  int64_t cap = (int64_t)sm_count() * (TRAIN ? 1 : blocks_per_sm(kernel, 256, smem));
   if (cap > kHeadMaxGrid) cap = kHeadMaxGrid;
   const int grid = (int)(want < cap ? want : cap);
-  kernel<<<grid, NW * 32, smem, stream>>>(p);
+  kernel<<<grid, 256, smem, stream>>>(p);
   IA_LAUNCH_CHECK();
   if (TRAIN && (dw || db)) {
     const float* partials = reinterpret_cast<const float*>(static_cast<const char*>(p.workspace) + kWorkspaceBytes);
@@ -288,18 +325,21 @@ template <typename T, typename G, bool TRAIN, int VPL>
 static int launch_head_one(const HeadParams& p, cudaStream_t stream, float* dw, float* db) {
   constexpr int P4 = VPL * 32 * (VecTraits<T>::kElems / 4);
   const size_t w_bytes = (size_t)(TRAIN ? 6 : 4) * P4 * 16;
-  if (!TRAIN) return launch_head_nw<T, G, false, VPL, 8>(p, 1, w_bytes, stream, dw, db);
+  if (!TRAIN) return launch_head_rr<T, G, false, VPL, 1>(p, 1, w_bytes, stream, dw, db);
   const size_t fixed = w_bytes + (size_t)(((2 * p.h + 3) & ~3)) * 4;
   const size_t row_bytes = (size_t)p.h * sizeof(T);
-  auto fit = [&](int nw) {   // deepest ring (>= 2 stages) that fits next to the W tiles
+  auto fit = [&](int rr) {   // deepest ring that fits next to the W tiles (8 warps)
     int st = kHeadMaxStages;
-    while (st > 1 && fixed + (size_t)nw * st * (2 * row_bytes + 8) > 227 * 1024) --st;
-    return st;
+    while (st > 1 && fixed + (size_t)8 * st * rr * 2 * row_bytes > 227 * 1024) --st;
+    return (fixed + (size_t)8 * st * rr * 2 * row_bytes <= 227 * 1024) ? st : 0;
   };
-  const int st16 = fit(16), st8 = fit(8);
-  if (st16 >= 2) return launch_head_nw<T, G, true, VPL, 16>(p, st16, fixed + (size_t)16 * st16 * (2 * row_bytes + 8), stream, dw, db);
-  if (st8 >= 2 || fixed + (size_t)8 * (2 * row_bytes + 8) <= 227 * 1024)
-    return launch_head_nw<T, G, true, VPL, 8>(p, st8, fixed + (size_t)8 * st8 * (2 * row_bytes + 8), stream, dw, db);
+  // two rows per W read when the rows are small enough to keep both in registers (VPL <= 4) and the ring has >= 2 stages
+  if (VPL <= 4 && p.n >= 4096) {
+    const int st2 = fit(2);
+    if (st2 >= 2) return launch_head_rr<T, G, true, (VPL <= 4 ? VPL : 4), 2>(p, st2, fixed + (size_t)8 * st2 * 2 * 2 * row_bytes, stream, dw, db);
+  }
+  const int st1 = fit(1);
+  if (st1 >= 1) return launch_head_rr<T, G, true, VPL, 1>(p, st1, fixed + (size_t)8 * st1 * 2 * row_bytes, stream, dw, db);
   set_error("h too large for the shared-memory W tile + row ring");
   return IA_ERR_UNSUPPORTED;
 }
