@@ -73,13 +73,25 @@ __global__ void __launch_bounds__(256, 1) softmax_head_kernel(const HeadParams p
   float* sw = reinterpret_cast<float*>(smem4);
   float* sacc = sw + 24 * P4;
   const int h = p.h, h2 = 2 * p.h;
-  for (int i = threadIdx.x; i < h2; i += blockDim.x) {
-    const int half = i >= h, e = half ? i - h : i;
-    const int pos = half * (4 * P4) + swz<E>(e);
-    const float a = p.w[i], c = p.w[h2 + i];
-    sw[pos] = a;
-    sw[8 * P4 + pos] = c;
-    if (TRAIN) { sw[16 * P4 + pos] = c - a; sacc[i] = 0.f; }
+  for (int i0 = threadIdx.x; i0 < h2; i0 += 4 * blockDim.x) {   // four independent loads in flight per thread
+    float a[4], c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      a[u] = i < h2 ? __ldg(p.w + i) : 0.f;
+      c[u] = i < h2 ? __ldg(p.w + h2 + i) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < h2) {
+        const int half = i >= h, e = half ? i - h : i;
+        const int pos = half * (4 * P4) + swz<E>(e);
+        sw[pos] = a[u];
+        sw[8 * P4 + pos] = c[u];
+        if (TRAIN) { sw[16 * P4 + pos] = c[u] - a[u]; sacc[i] = 0.f; }
+      }
+    }
   }
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warps_total = (int64_t)gridDim.x * NW;
@@ -133,6 +145,9 @@ __global__ void __launch_bounds__(256, 1) softmax_head_kernel(const HeadParams p
     int64_t rows[RR];
 #pragma unroll
     for (int k = 0; k < RR; ++k) { rows[k] = grp * RR + k; live[k] = rows[k] < p.n; }
+    int label[RR];
+#pragma unroll
+    for (int k = 0; k < RR; ++k) label[k] = (TRAIN && live[k]) ? (int)(__ldg(p.labels + rows[k]) != 0) : 0;   // issued early: L2 latency hides behind the ring wait
     if (TRAIN) {
       if (p.stages == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
       else if (p.stages == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
@@ -204,9 +219,8 @@ __global__ void __launch_bounds__(256, 1) softmax_head_kernel(const HeadParams p
           if (p.probs) { p.probs[2 * rows[k]] = p0; p.probs[2 * rows[k] + 1] = p1; }
         }
         if (TRAIN) {
-          const int label = (int)(__ldg(p.labels + rows[k]) != 0);
-          loss_acc += logf(den) - ((label ? z1 : z0) - m);         // -log softmax[label]
-          delta[k] = (label ? -p0 : p1) * p.grad_scale;             // d loss / d logit1 ( = -d loss / d logit0 )
+          loss_acc += logf(den) - ((label[k] ? z1 : z0) - m);      // -log softmax[label]
+          delta[k] = (label[k] ? -p0 : p1) * p.grad_scale;          // d loss / d logit1 ( = -d loss / d logit0 )
           db_acc += delta[k];
         }
       }
@@ -247,22 +261,49 @@ __global__ void __launch_bounds__(256, 1) softmax_head_kernel(const HeadParams p
 
   if (TRAIN) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    // fixed-order block reduction of the per-lane dW accumulators: warp 0, then warp 1, ...
-    for (int w = 0; w < NW; ++w) {
-      if (wib == w) {
+    // block reduction of the per-lane dW accumulators in a FIXED order (warp 0 + warp 1 + ...), done in parallel:
+    // every warp parks its accumulators in the (now idle) ring memory, then each thread adds the NW values of its
+    // columns.  Needs NW * 2h floats of ring space (always true for >= 1 stage of 16-bit rows x 2 or fp32 rows).
+    __syncthreads();
+    float* park = reinterpret_cast<float*>(ring_base);
+    const bool park_fits = (size_t)NW * h2 * sizeof(float) <= (size_t)NW * p.stages * stage_bytes;
+    if (park_fits) {
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-          const int v = lane + 32 * i;
-          if (v < nvec) {
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) {
 #pragma unroll
-            for (int j = 0; j < E; ++j) {
-              sacc[v * E + j] += accx[i * E + j];
-              sacc[h + v * E + j] += accy[i * E + j];
-            }
+          for (int j = 0; j < E; j += 4) {
+            *reinterpret_cast<float4*>(park + (size_t)wib * h2 + v * E + j) = make_float4(accx[i * E + j], accx[i * E + j + 1], accx[i * E + j + 2], accx[i * E + j + 3]);
+            *reinterpret_cast<float4*>(park + (size_t)wib * h2 + h + v * E + j) = make_float4(accy[i * E + j], accy[i * E + j + 1], accy[i * E + j + 2], accy[i * E + j + 3]);
           }
         }
       }
       __syncthreads();
+      for (int c = threadIdx.x; c < h2; c += blockDim.x) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) a += park[(size_t)w * h2 + c];
+        sacc[c] = a;
+      }
+      __syncthreads();
+    } else {
+      for (int w = 0; w < NW; ++w) {
+        if (wib == w) {
+#pragma unroll
+          for (int i = 0; i < VPL; ++i) {
+            const int v = lane + 32 * i;
+            if (v < nvec) {
+#pragma unroll
+              for (int j = 0; j < E; ++j) {
+                sacc[v * E + j] += accx[i * E + j];
+                sacc[h + v * E + j] += accy[i * E + j];
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
     }
     __shared__ float wl[NW], wdb[NW];
     if (lane == 0) { wl[wib] = loss_acc; wdb[wib] = db_acc; }
@@ -280,17 +321,22 @@ __global__ void __launch_bounds__(256, 1) softmax_head_kernel(const HeadParams p
   }
 }
 
-// dW[1][j] = sum over blocks (index order) of partial[b][j]; dW[0] = -dW[1]; same for db.
+// dW[1][j] = sum over blocks of partial[b][j] (fixed order: lane-strided partial sums, then a shuffle tree);
+// dW[0] = -dW[1]; same for db.  One warp per column.
 __global__ void __launch_bounds__(256) softmax_head_finalize(const float* partials, int nblocks, int h2, float* dw,
                                                              float* db) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (j > h2) return;
   float acc = 0.f;
-  for (int b = 0; b < nblocks; ++b) acc += partials[(size_t)b * (h2 + 2) + j];
-  if (j < h2) {
-    if (dw) { dw[h2 + j] = acc; dw[j] = -acc; }
-  } else if (db) {
-    db[1] = acc; db[0] = -acc;
+  for (int b = lane; b < nblocks; b += 32) acc += partials[(size_t)b * (h2 + 2) + j];
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    if (j < h2) {
+      if (dw) { dw[h2 + j] = acc; dw[j] = -acc; }
+    } else if (db) {
+      db[1] = acc; db[0] = -acc;
+    }
   }
 }
 
@@ -315,7 +361,7 @@ static int launch_head_rr(const HeadParams& p_in, int stages, size_t smem, cudaS
   if (TRAIN && (dw || db)) {
     const float* partials = reinterpret_cast<const float*>(static_cast<const char*>(p.workspace) + kWorkspaceBytes);
     const int h2 = 2 * p.h;
-    softmax_head_finalize<<<(h2 + 1 + 255) / 256, 256, 0, stream>>>(partials, grid, h2, dw, db);
+    softmax_head_finalize<<<(h2 + 1 + 7) / 8, 256, 0, stream>>>(partials, grid, h2, dw, db);
     IA_LAUNCH_CHECK();
   }
   return IA_OK;
