@@ -137,6 +137,9 @@ __global__ void __launch_bounds__(256, 1) softmax_head_kernel(const HeadParams p
   }
   float loss_acc = 0.f, db_acc = 0.f;
 
+  long long label_next[RR];
+#pragma unroll
+  for (int k = 0; k < RR; ++k) label_next[k] = (TRAIN && grp0 * RR + k < p.n) ? __ldg(p.labels + grp0 * RR + k) : 0;
   int it = 0;
   for (int64_t grp = grp0; grp < n_groups; grp += warps_total, ++it) {
     const int stage = TRAIN ? it % p.stages : 0;
@@ -145,9 +148,14 @@ __global__ void __launch_bounds__(256, 1) softmax_head_kernel(const HeadParams p
     int64_t rows[RR];
 #pragma unroll
     for (int k = 0; k < RR; ++k) { rows[k] = grp * RR + k; live[k] = rows[k] < p.n; }
-    int label[RR];
+    long long label[RR];   // this group's labels were loaded one iteration ago (software pipelined: L2 latency off the path)
 #pragma unroll
-    for (int k = 0; k < RR; ++k) label[k] = (TRAIN && live[k]) ? (int)(__ldg(p.labels + rows[k]) != 0) : 0;   // issued early: L2 latency hides behind the ring wait
+    for (int k = 0; k < RR; ++k) label[k] = label_next[k];
+    if (TRAIN) {
+      const int64_t gn = grp + warps_total;
+#pragma unroll
+      for (int k = 0; k < RR; ++k) label_next[k] = (gn * RR + k < p.n) ? __ldg(p.labels + gn * RR + k) : 0;
+    }
     if (TRAIN) {
       if (p.stages == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
       else if (p.stages == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
@@ -219,8 +227,8 @@ __global__ void __launch_bounds__(256, 1) softmax_head_kernel(const HeadParams p
           if (p.probs) { p.probs[2 * rows[k]] = p0; p.probs[2 * rows[k] + 1] = p1; }
         }
         if (TRAIN) {
-          loss_acc += logf(den) - ((label[k] ? z1 : z0) - m);      // -log softmax[label]
-          delta[k] = (label[k] ? -p0 : p1) * p.grad_scale;          // d loss / d logit1 ( = -d loss / d logit0 )
+          loss_acc += logf(den) - ((label[k] != 0 ? z1 : z0) - m);      // -log softmax[label]
+          delta[k] = (label[k] != 0 ? -p0 : p1) * p.grad_scale;          // d loss / d logit1 ( = -d loss / d logit0 )
           db_acc += delta[k];
         }
       }
