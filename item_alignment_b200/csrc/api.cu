@@ -36,16 +36,8 @@ static bool aligned16(const void* p, int64_t ld_elems, size_t esize) {
   return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && ((ld_elems * (int64_t)esize) % 16 == 0);
 }
 
-static int pair_flags() {
-  static int f = -1;
-  if (f < 0) { const char* e = getenv("IA_PAIR_FLAGS"); f = e ? atoi(e) : 0; }
-  return f;
-}
-
-static int dispatch_pair(int mode, bool cosloss, int measure, int dtype, int grad_dtype, const PairParams& p_in,
+static int dispatch_pair(int mode, bool cosloss, int measure, int dtype, int grad_dtype, const PairParams& p,
                          cudaStream_t stream) {
-  PairParams p = p_in;
-  p.flags = pair_flags();
   const size_t es = dtype_size(dtype), gs = dtype_size(grad_dtype);
   const int elems = dtype == IA_F32 ? 4 : 8;
   bool vec_ok = (p.d % elems == 0) && aligned16(p.x, p.ldx, es) && aligned16(p.y, p.ldy, es);

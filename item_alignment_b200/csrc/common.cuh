@@ -69,16 +69,6 @@ __device__ __forceinline__ void stg_stream(uint4* p, const uint4& v) {
                : "memory");
 }
 
-// experiment variants (cache operators): .cs = streaming / evict-first
-__device__ __forceinline__ uint4 ldg_cs(const uint4* p) {
-  uint4 r;
-  asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ void stg_cs(uint4* p, const uint4& v) {
-  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
 // unpack one 128-bit vector into kElems floats
 template <typename T> __device__ __forceinline__ void unpack(const uint4& v, float* f);
 template <> __device__ __forceinline__ void unpack<float>(const uint4& v, float* f) {
@@ -102,43 +92,39 @@ template <> __device__ __forceinline__ void unpack<__half>(const uint4& v, float
 }
 
 // pack floats back (round to nearest even) and store; NF = number of floats (4 or 8)
-// streaming store with a runtime choice of cache operator (cs != 0: st.global.cs)
-__device__ __forceinline__ void stg_sel(uint4* p, const uint4& v, int cs) {
-  if (cs) stg_cs(p, v); else stg_stream(p, v);
-}
 template <typename G, int NF> struct Packer;
 template <> struct Packer<float, 4> {
-  static __device__ __forceinline__ void store(float* dst, const float* f, int cs = 0) {
-    stg_sel(reinterpret_cast<uint4*>(dst), make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]),
-                                                      __float_as_uint(f[2]), __float_as_uint(f[3])), cs);
+  static __device__ __forceinline__ void store(float* dst, const float* f) {
+    stg_stream(reinterpret_cast<uint4*>(dst), make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]),
+                                                         __float_as_uint(f[2]), __float_as_uint(f[3])));
   }
 };
 template <> struct Packer<float, 8> {
-  static __device__ __forceinline__ void store(float* dst, const float* f, int cs = 0) {
-    Packer<float, 4>::store(dst, f, cs);
-    Packer<float, 4>::store(dst + 4, f + 4, cs);
+  static __device__ __forceinline__ void store(float* dst, const float* f) {
+    Packer<float, 4>::store(dst, f);
+    Packer<float, 4>::store(dst + 4, f + 4);
   }
 };
 template <> struct Packer<__nv_bfloat16, 8> {
-  static __device__ __forceinline__ void store(__nv_bfloat16* dst, const float* f, int cs = 0) {
+  static __device__ __forceinline__ void store(__nv_bfloat16* dst, const float* f) {
     uint4 v;
     __nv_bfloat162 t;
     t = __floats2bfloat162_rn(f[0], f[1]); v.x = *reinterpret_cast<uint32_t*>(&t);
     t = __floats2bfloat162_rn(f[2], f[3]); v.y = *reinterpret_cast<uint32_t*>(&t);
     t = __floats2bfloat162_rn(f[4], f[5]); v.z = *reinterpret_cast<uint32_t*>(&t);
     t = __floats2bfloat162_rn(f[6], f[7]); v.w = *reinterpret_cast<uint32_t*>(&t);
-    stg_sel(reinterpret_cast<uint4*>(dst), v, cs);
+    stg_stream(reinterpret_cast<uint4*>(dst), v);
   }
 };
 template <> struct Packer<__half, 8> {
-  static __device__ __forceinline__ void store(__half* dst, const float* f, int cs = 0) {
+  static __device__ __forceinline__ void store(__half* dst, const float* f) {
     uint4 v;
     __half2 t;
     t = __floats2half2_rn(f[0], f[1]); v.x = *reinterpret_cast<uint32_t*>(&t);
     t = __floats2half2_rn(f[2], f[3]); v.y = *reinterpret_cast<uint32_t*>(&t);
     t = __floats2half2_rn(f[4], f[5]); v.z = *reinterpret_cast<uint32_t*>(&t);
     t = __floats2half2_rn(f[6], f[7]); v.w = *reinterpret_cast<uint32_t*>(&t);
-    stg_sel(reinterpret_cast<uint4*>(dst), v, cs);
+    stg_stream(reinterpret_cast<uint4*>(dst), v);
   }
 };
 

@@ -40,7 +40,6 @@ struct PairParams {
   float grad_scale;            // upstream * (1/n for mean)
   double loss_scale;           // 1/n for mean, 1 otherwise
   void* workspace;
-  int flags;                   // experiments: bit0 st.global.cs for gradients, bit1 ld.global.cs for inputs
 };
 
 // Per-pair sums gathered in one sweep over the registers.
@@ -182,8 +181,8 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
         for (int i = 0; i < VPL; ++i) {
           const int v = lane + 32 * i;
           if (live[k] && v < nvec) {
-            if (p.flags & 2) { xv[k][i] = ldg_cs(xr + v); yv[k][i] = ldg_cs(yr + v); }
-            else { xv[k][i] = ldg_stream(xr + v); yv[k][i] = ldg_stream(yr + v); }
+            xv[k][i] = ldg_stream(xr + v);
+            yv[k][i] = ldg_stream(yr + v);
           } else {
             xv[k][i] = make_uint4(0, 0, 0, 0);
             yv[k][i] = make_uint4(0, 0, 0, 0);
@@ -285,8 +284,8 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
                 gy[j] = -gx[j];
               }
             }
-            Packer<G, E>::store(dxr + (int64_t)v * E, gx, p.flags & 1);
-            Packer<G, E>::store(dyr + (int64_t)v * E, gy, p.flags & 1);
+            Packer<G, E>::store(dxr + (int64_t)v * E, gx);
+            Packer<G, E>::store(dyr + (int64_t)v * E, gy);
           }
         }
       }

@@ -39,8 +39,8 @@ struct RetrParams {
   uint32_t* done;       // [n_items*4] set when a warp's quarter of an item's lists is final
   unsigned long long* stats;  // [8] appends, compactions, rare groups, rare blocks (telemetry)
   uint32_t row_base;    // global row id of catalog row 0 (shard offset)
-  int flags;            // tuning switches for in-run A/B measurements (env IA_RETR_FLAGS): bit0 merge variant,
-                        // bit1 early tau load, bit2 finished-split bound, bit3 paced merges (<= 2 lanes per tile after release)
+  int flags;            // tuning switches for in-run A/B measurements (env IA_RETR_FLAGS, default 14): bit1 early tau
+                        // load, bit2 finished-split bound, bit3 paced merges (<= 2 lanes per tile after release)
 };
 
 // A valid lower bound on the final k-th best key of a query from the FINISHED splits of its query tile:

@@ -1,4 +1,4 @@
-"""Cache-operator experiment for the fused pair kernel: honest setting = outputs alternate between two buffer sets."""
+"""Row-grouping experiment for the fused pair kernel (IA_PAIR_ROWS=1|2): outputs alternate between two buffer sets."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
