@@ -57,7 +57,7 @@ constexpr int kHeadMaxStages = 4;   // rows in flight per warp in the bulk-copy 
 // (Measured first: a cp.async.bulk ring and a 16-warp variant both sat at 55 % -- the W re-reads were the limit.)
 // The forward-only kernel is light: plain streaming loads, RR = 1.
 template <typename T, typename G, bool TRAIN, int VPL, int RR>
-__global__ void __launch_bounds__(256, 1) softmax_head_kernel(const HeadParams p) {
+__global__ void __launch_bounds__(256, TRAIN ? 1 : 2) softmax_head_kernel(const HeadParams p) {
   constexpr int NW = 8;
   constexpr int E = VecTraits<T>::kElems;
   constexpr int C = E / 4;            // float4 chunks per 128-bit input vector
@@ -174,13 +174,16 @@ __global__ void __launch_bounds__(256, 1) softmax_head_kernel(const HeadParams p
       }
       arm(stage, grp + (int64_t)p.stages * warps_total);   // the slot is in registers now: refill it
     } else {
-      const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + rows[0] * p.ldx);
-      const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + rows[0] * p.ldy);
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) {
-        const int v = lane + 32 * i;
-        if (v < nvec) { xv[0][i] = ldg_stream(xr + v); yv[0][i] = ldg_stream(yr + v); }
-        else { xv[0][i] = make_uint4(0, 0, 0, 0); yv[0][i] = make_uint4(0, 0, 0, 0); }
+      for (int k = 0; k < RR; ++k) {
+        const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + rows[k] * p.ldx);
+        const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + rows[k] * p.ldy);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const int v = lane + 32 * i;
+          if (live[k] && v < nvec) { xv[k][i] = ldg_stream(xr + v); yv[k][i] = ldg_stream(yr + v); }
+          else { xv[k][i] = make_uint4(0, 0, 0, 0); yv[k][i] = make_uint4(0, 0, 0, 0); }
+        }
       }
     }
     // ---- logits: every W chunk is read once and applied to all RR rows
@@ -379,7 +382,10 @@ template <typename T, typename G, bool TRAIN, int VPL>
 static int launch_head_one(const HeadParams& p, cudaStream_t stream, float* dw, float* db) {
   constexpr int P4 = VPL * 32 * (VecTraits<T>::kElems / 4);
   const size_t w_bytes = (size_t)(TRAIN ? 6 : 4) * P4 * 16;
-  if (!TRAIN) return launch_head_rr<T, G, false, VPL, 1>(p, 1, w_bytes, stream, dw, db);
+  if (!TRAIN) {   // forward only: two adjacent rows per W read when both fit in registers (halves the shared-memory traffic)
+    if (VPL <= 4 && p.n >= 4096) return launch_head_rr<T, G, false, (VPL <= 4 ? VPL : 4), 2>(p, 1, w_bytes, stream, dw, db);
+    return launch_head_rr<T, G, false, VPL, 1>(p, 1, w_bytes, stream, dw, db);
+  }
   const size_t fixed = w_bytes + (size_t)(((2 * p.h + 3) & ~3)) * 4;
   const size_t row_bytes = (size_t)p.h * sizeof(T);
   auto fit = [&](int rr) {   // deepest ring that fits next to the W tiles (8 warps)
