@@ -616,7 +616,7 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // 2-D row-major [rows, d] 16-bit matrix, box = 64 columns (128 B, swizzle 128B) x box_rows rows
-static int make_tmap(CUtensorMap* map, int dtype, const void* base, int64_t rows, int64_t d, int64_t ld, int box_rows) {
+int make_tmap(CUtensorMap* map, int dtype, const void* base, int64_t rows, int64_t d, int64_t ld, int box_rows) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) { set_error("cuTensorMapEncodeTiled not available from the driver"); return IA_ERR_CUDA; }
   const cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};

@@ -290,6 +290,61 @@ def row_inv_norm(x, eps=1e-8):
     return out
 
 
+def _prep_project(f1, f2, w, b):
+    if not (f1.is_cuda and f2.is_cuda and w.is_cuda):
+        raise RuntimeError("item_alignment_b200 runs on CUDA tensors only (no CPU fallback)")
+    if f1.dim() != 2 or f1.shape != f2.shape or w.dim() != 2 or w.shape[1] != f1.shape[1]:
+        raise ValueError(f"expected features [N, K] x2 and weight [H, K], got {tuple(f1.shape)}, {tuple(f2.shape)}, {tuple(w.shape)}")
+    if f1.dtype not in (torch.bfloat16, torch.float16):
+        raise NotImplementedError("the fused projection runs bf16 / fp16 features on the tensor cores; keep torch for fp32")
+    f2 = f2.to(f1.dtype)
+    w = w.detach().to(f1.dtype)            # nn.Linear under autocast casts its fp32 master weight the same way
+    f1, f2, w = (t if (t.stride(1) == 1 and t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0) else t.contiguous() for t in (f1, f2, w))
+    if b is not None:
+        b = b.detach().to(torch.float32).contiguous()
+    return f1, f2, w, b
+
+
+def project_tanh_raw(f1, f2, w, b):
+    """x = tanh(f1 @ w.T + b), y = tanh(f2 @ w.T + b) from ONE tcgen05 GEMM launch (reference base.py:67-75 with
+    dropout inactive); outputs in the feature dtype."""
+    f1, f2, w, b = _prep_project(f1, f2, w, b)
+    n, k = f1.shape
+    h = w.shape[0]
+    x = torch.empty((n, h), dtype=f1.dtype, device=f1.device)
+    y = torch.empty((n, h), dtype=f1.dtype, device=f1.device)
+    with torch.cuda.device(f1.device):
+        check(lib().ia_project_tanh_fwd(_DT[f1.dtype], f1.data_ptr(), f2.data_ptr(), _ld(f1), _ld(f2), n, k, w.data_ptr(), _ld(w),
+                                        b.data_ptr() if b is not None else None, h, x.data_ptr(), y.data_ptr(), h, h, _stream()))
+    return x, y
+
+
+def project_score_raw(measure, f1, f2, w, b, threshold=None, want_embeds=False):
+    """Projection + pair score in one launch (+ a [N]-sized finalize): (sim, probs, labels, x, y).  With
+    want_embeds=False the embeddings never reach HBM."""
+    f1, f2, w, b = _prep_project(f1, f2, w, b)
+    n, k = f1.shape
+    h = w.shape[0]
+    dev = f1.device
+    x = torch.empty((n, h), dtype=f1.dtype, device=dev) if want_embeds else None
+    y = torch.empty((n, h), dtype=f1.dtype, device=dev) if want_embeds else None
+    sim = torch.empty(n, dtype=torch.float32, device=dev)
+    probs = torch.empty(n, dtype=torch.float32, device=dev)
+    labels = torch.empty(n, dtype=torch.bool, device=dev) if threshold is not None else None
+    mid = _measure_id(measure)
+    if measure == "softmax":
+        raise ValueError(f"Unsupported similarty measure: {measure}")
+    with torch.cuda.device(dev):
+        need = lib().ia_project_score_workspace_bytes(n, k, h)
+        ws = torch.empty(max(int(need), 16), dtype=torch.uint8, device=dev)
+        check(lib().ia_project_score_fwd(mid, _DT[f1.dtype], f1.data_ptr(), f2.data_ptr(), _ld(f1), _ld(f2), n, k, w.data_ptr(),
+                                         _ld(w), b.data_ptr() if b is not None else None, h,
+                                         x.data_ptr() if want_embeds else None, y.data_ptr() if want_embeds else None, h, h,
+                                         sim.data_ptr(), probs.data_ptr(), float(threshold) if threshold is not None else 0.0,
+                                         labels.data_ptr() if labels is not None else None, ws.data_ptr(), ws.numel(), _stream()))
+    return sim, probs, labels, x, y
+
+
 # ------------------------------------------------------------------------------------------- autograd
 class _PairScoreFn(torch.autograd.Function):
     """sim = similarity(x, y) with the backward kernel (unfused head -> loss module sequence of the reference)."""
@@ -386,6 +441,32 @@ class _FusedSoftmaxCEFn(torch.autograd.Function):
         return dx, dy, dw.to(ctx.wdtype), db.to(ctx.bdtype), None
 
 
+class _ProjectTanhFn(torch.autograd.Function):
+    """(x, y) = tanh(dense(f1)), tanh(dense(f2)) on the fused GEMM; the backward is plain library GEMMs
+    (d_pre = g * (1 - out^2); dW = d_pre^T f, db = sum d_pre, df = d_pre W), SURVEY 8 row a6."""
+
+    @staticmethod
+    def forward(ctx, f1, f2, w, b):
+        x, y = project_tanh_raw(f1, f2, w, b)
+        ctx.save_for_backward(f1, f2, w, x, y)
+        ctx.has_bias = b is not None
+        ctx.bdtype = b.dtype if b is not None else None
+        return x, y
+
+    @staticmethod
+    def backward(ctx, gx, gy):
+        f1, f2, w, x, y = ctx.saved_tensors
+        cd = x.dtype
+        p1 = (gx.float() * (1.0 - x.float() ** 2)).to(cd)
+        p2 = (gy.float() * (1.0 - y.float() ** 2)).to(cd)
+        wc = w.to(cd)
+        df1 = (p1 @ wc).to(f1.dtype) if ctx.needs_input_grad[0] else None
+        df2 = (p2 @ wc).to(f2.dtype) if ctx.needs_input_grad[1] else None
+        dw = (p1.t() @ f1.to(cd) + p2.t() @ f2.to(cd)).to(w.dtype) if ctx.needs_input_grad[2] else None
+        db = (p1.float().sum(0) + p2.float().sum(0)).to(ctx.bdtype) if (ctx.has_bias and ctx.needs_input_grad[3]) else None
+        return df1, df2, dw, db
+
+
 # ------------------------------------------------------------------------------------------- public
 def pair_similarity(measure, x, y):
     """similarity(x, y) -> [N] fp32, differentiable (reference base.py:54-62,77)."""
@@ -452,3 +533,18 @@ def softmax_head_ce(x, y, w, b, labels):
     x, y = _prep(x, y)
     loss, logits, probs = _FusedSoftmaxCEFn.apply(x, y, w, b, labels)
     return logits, probs, loss
+
+
+def project_tanh(f1, f2, w, b):
+    """(x, y) = tanh(linear(f1, w, b)), tanh(linear(f2, w, b)), differentiable (reference base.py:67-75, eval mode)."""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (f1, f2, w, b)):
+        return _ProjectTanhFn.apply(f1, f2, w, b)
+    return project_tanh_raw(f1, f2, w, b)
+
+
+def project_score(measure, f1, f2, w, b, threshold=None, want_embeds=False):
+    """Inference: projection + similarity + probability map (+ threshold labels) from the encoder features in one
+    launch.  Returns (sim, probs[, labels]) or, with want_embeds, (x, y, sim, probs[, labels])."""
+    sim, probs, labels, x, y = project_score_raw(measure, f1, f2, w, b, threshold, want_embeds)
+    out = (sim, probs) if threshold is None else (sim, probs, labels)
+    return ((x, y) + out) if want_embeds else out

@@ -5,7 +5,9 @@ src/models/base.py, with the similarity / probability / loss arithmetic on the s
     TwoTowerClassificationHead(h, dropout, num_labels)     -> (x, y, logits, probs)   base.py:96-117
     InnerProduct(normalize=False).forward(x1, x2)          -> [N]                     base.py:25-34
 
-The dense -> tanh projection of the VecSim head stays on cuBLAS/ATen (boundary-adjacent).
+The dense -> tanh projection of the VecSim head runs as one tcgen05 GEMM with bias + tanh in its epilogue
+(csrc/projection.cu) for bf16 / fp16 features when dropout is inactive, and on cuBLAS/ATen otherwise (SURVEY 8
+row a6: boundary-adjacent).
 `forward_with_loss` is the fused single-pass entry the reference's forward() can call instead of
 classifier(...) + the loss ladder.
 """
@@ -77,20 +79,47 @@ class VecSimClassificationHead(nn.Module):
         x = torch.tanh(x)
         return self.dropout(x)
 
+    def _fused_dtype(self, f1, f2):
+        """dtype the fused tcgen05 projection would run in, or None when the library path must be used: dropout
+        active (torch's RNG stream cannot be reproduced inside the GEMM), fp32 arithmetic, or odd shapes."""
+        if self.training and self.dropout.p > 0:
+            return None
+        if not (f1.is_cuda and f2.is_cuda) or f1.dim() != 2 or f1.shape != f2.shape:
+            return None
+        dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else f1.dtype
+        if dt not in (torch.bfloat16, torch.float16):
+            return None
+        if not torch.is_autocast_enabled("cuda") and self.dense.weight.dtype != dt:
+            return None
+        k, h = self.dense.in_features, self.dense.out_features
+        return dt if (f1.shape[1] == k and k % 8 == 0 and h % 8 == 0 and h <= 4096) else None
+
+    def project_pair(self, features_1, features_2):
+        """Both sides through dense -> tanh: one fused GEMM launch when possible."""
+        dt = self._fused_dtype(features_1, features_2)
+        if dt is None:
+            return self.project(features_1), self.project(features_2)
+        return F_.project_tanh(features_1.to(dt), features_2.to(dt), self.dense.weight, self.dense.bias)
+
     def forward(self, features_1, features_2):
-        x = self.project(features_1)
-        y = self.project(features_2)
         measure = self.config.similarity_measure
         if measure not in ("cosine", "l1", "l2", "inner_product"):
             raise ValueError(f"Unsupported similarty measure: {measure}")
+        dt = self._fused_dtype(features_1, features_2)
+        needs_grad = torch.is_grad_enabled() and (
+            features_1.requires_grad or features_2.requires_grad or self.dense.weight.requires_grad)
+        if dt is not None and not needs_grad:
+            # inference: projection, score and probability map in one launch
+            return F_.project_score(measure, features_1.to(dt), features_2.to(dt), self.dense.weight, self.dense.bias,
+                                    want_embeds=True)
+        x, y = self.project_pair(features_1, features_2)
         sim, probs = F_.pair_score(measure, x, y)
         return x, y, sim, probs
 
     def forward_with_loss(self, features_1, features_2, labels, loss_type, margin=1.0):
         """Head + loss ladder (reference text.py:1468-1477) + their backward in one HBM pass.
         Returns (x, y, sim, probs, loss); loss.backward() continues into dense/tanh through autograd."""
-        x = self.project(features_1)
-        y = self.project(features_2)
+        x, y = self.project_pair(features_1, features_2)
         sim, probs, loss = F_.pair_score_loss(self.config.similarity_measure, loss_type, x, y, labels, margin)
         return x, y, sim, probs, loss
 
