@@ -139,7 +139,7 @@ int ia_scale_inplace(int dtype, void* a, void* b, int64_t count, const float* g,
  * base.py:47-49) -- one tcgen05 GEMM for both sides with bias + tanh + rounding in its epilogue.
  * f1, f2: [n, k_in]; w: [h, k_in] (nn.Linear layout); bias: [h] fp32 or NULL; x, y: [n, h] in `dtype`.
  * dtype is IA_BF16 or IA_F16 (fp32 -> IA_ERR_UNSUPPORTED: keep torch's GEMM); k_in, h and all leading
- * dimensions are multiples of 8 elements, pointers 16-byte aligned, h <= 4096. */
+ * dimensions are multiples of 8 elements, pointers 16-byte aligned. */
 int ia_project_tanh_fwd(int dtype, const void* f1, const void* f2, int64_t ldf1, int64_t ldf2, int64_t n,
                         int64_t k_in, const void* w, int64_t ldw, const float* bias, int64_t h, void* x,
                         void* y, int64_t ldx, int64_t ldy, ia_stream_t stream);
@@ -148,6 +148,10 @@ int ia_project_tanh_fwd(int dtype, const void* f1, const void* f2, int64_t ldf1,
  * order); x and y may be NULL, in which case the embeddings never reach HBM (inference scoring).
  * workspace: ia_project_score_workspace_bytes(n, k_in, h) bytes of device scratch, no initialisation. */
 size_t ia_project_score_workspace_bytes(int64_t n, int64_t k_in, int64_t h);
+/* Diagnostics: cycle counters of the last projection launch made with IA_PROJ_DEBUG=2 in the environment
+ * (summed over CTAs): [0] MMA thread waiting for the epilogue, [1] for TMA, [2] MMA thread total,
+ * [3] epilogue warps waiting for the MMAs, [4] epilogue warps total. */
+int ia_project_last_stats(uint64_t* out8);
 int ia_project_score_fwd(int measure, int dtype, const void* f1, const void* f2, int64_t ldf1, int64_t ldf2,
                          int64_t n, int64_t k_in, const void* w, int64_t ldw, const float* bias, int64_t h,
                          void* x, void* y, int64_t ldx, int64_t ldy, float* sim, float* probs,

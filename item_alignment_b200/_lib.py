@@ -47,6 +47,7 @@ SIGNATURES = {
     "ia_scale_inplace": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "ia_project_tanh_fwd": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p,
                                     c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "ia_project_last_stats": (c_int, [c_void_p]),
     "ia_project_score_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "ia_project_score_fwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64,
                                      c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_double,

@@ -2,18 +2,20 @@
 // shared `dense` of VecSimClassificationHead (reference src/models/base.py:47-49,67-75; dropout inactive), and,
 // optionally, the pair score of (x, y) computed in the same epilogue so that inference never writes the embeddings.
 //
-// Persistent, warp-specialised tcgen05 GEMM, one CTA per SM, 192 threads:
+// Persistent, warp-specialised tcgen05 GEMM, one CTA per SM, 320 threads:
 //   warp 0 (one lane)  TMA producer: per K block one 128x64 box of f1, one of f2 and one 128x64 box of W
 //                      (128B swizzle) -> a 48 KB stage, 4 stages, full/empty mbarriers;
-//   warp 1 (one lane)  tcgen05.mma M=128 x N=128 x K=16, two per K step (f1.W^T and f2.W^T share the W tile),
-//                      accumulators [x | y] = 256 TMEM columns, double-buffered in the 512 columns;
-//   warps 2-5          epilogue, one row per thread: tcgen05.ld -> + bias -> tanh -> round to the output type ->
-//                      128-bit stores, and (SCORE) the row sums of the pair score from the ROUNDED values, so the
-//                      result equals scoring the written embeddings.
+//   warp 1 (one lane)  tcgen05.mma M=128 (W rows = output columns) x N=256 ([f1 rows; f2 rows]) x K=16: the accumulator
+//                      is the TRANSPOSED [x | y] tile, 256 TMEM columns, double-buffered in the 512 columns;
+//   warps 2-9          epilogue (two warps per TMEM lane quarter, half of the pair rows each), one output column per thread: tcgen05.ld -> + bias -> tanh -> round to the output
+//                      type -> stores (a warp writes 64 contiguous bytes of a row), and (SCORE) the row sums of the
+//                      pair score from the ROUNDED values (butterfly transpose-reduce across the warp), so the result
+//                      equals scoring the written embeddings.
 // A CTA owns (row block, part) = `cts_per_part` consecutive 128-column tiles of one 128-row block; row sums of the parts
 // are combined in a fixed order by project_score_finalize (deterministic, no atomics).
 #include <cuda.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "pair_kernels.cuh"
@@ -26,9 +28,11 @@ int make_tmap(CUtensorMap* map, int dtype, const void* base, int64_t rows, int64
 namespace proj {
 constexpr int BM = 128, BN = 128, BK = 64, STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2, STAGE_BYTES = 2 * A_BYTES + W_BYTES;
-constexpr int THREADS = 192;
-constexpr int kMaxH = 4096;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kMaxH * 4 + 256 + 1024;
+constexpr int EPI_WARPS = 8;              // two per TMEM lane quarter: each takes half of the accumulator's columns
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
+constexpr int kMaxH = 65536;
+constexpr int SUMS_BYTES = 4 * BM * 16;   // per epilogue warp: one float4 of row sums per pair row of the block
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SUMS_BYTES + 256 + 1024;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 constexpr int kNoScore = -1;
 }  // namespace proj
@@ -40,7 +44,9 @@ struct ProjParams {
   void* x;             // [n, h] outputs in the input type; null = do not write the embeddings
   void* y;
   int64_t ldx, ldy;
-  float4* sums;        // SCORE: [parts][n] partial (xy, xx, yy, dist)
+  unsigned long long* stats;   // optional cycle counters (diagnostics): MMA waits on TMA / on the epilogue, epilogue waits
+  int debug_flags;
+  float4* sums;        // SCORE: [parts * 4 column quarters][n] partial (xy, xx, yy, dist)
 };
 
 // tanh to ~1e-6 relative (the output is rounded to 8 or 11 mantissa bits right after): 1 - 2/(e^{2a}+1) away from
@@ -56,37 +62,49 @@ __device__ __forceinline__ float tanh_f32(float v) {
   return copysignf(a < 0.1f ? small : big, v);
 }
 
-template <typename T> __device__ __forceinline__ uint4 pack8(const float* f);
-template <> __device__ __forceinline__ uint4 pack8<__nv_bfloat16>(const float* f) {
-  uint4 v;
-  __nv_bfloat162 t;
-  t = __floats2bfloat162_rn(f[0], f[1]); v.x = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2bfloat162_rn(f[2], f[3]); v.y = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2bfloat162_rn(f[4], f[5]); v.z = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2bfloat162_rn(f[6], f[7]); v.w = *reinterpret_cast<uint32_t*>(&t);
-  return v;
-}
-template <> __device__ __forceinline__ uint4 pack8<__half>(const float* f) {
-  uint4 v;
-  __half2 t;
-  t = __floats2half2_rn(f[0], f[1]); v.x = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2half2_rn(f[2], f[3]); v.y = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2half2_rn(f[4], f[5]); v.z = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2half2_rn(f[6], f[7]); v.w = *reinterpret_cast<uint32_t*>(&t);
-  return v;
+// sum over the 32 lanes of v[i] for every i: afterwards lane l holds the total of v[l] (returned).  Butterfly
+// transpose-reduce: 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int step = 16; step >= 1; step >>= 1) {
+    const bool up = (lane & step) != 0;
+#pragma unroll
+    for (int i = 0; i < step; ++i) {
+      const float send = up ? v[i] : v[i + step];
+      const float keep = up ? v[i + step] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+  }
+  return v[0];
 }
 
+template <typename T> __device__ __forceinline__ float round_to(float v, unsigned short& bits);
+template <> __device__ __forceinline__ float round_to<__nv_bfloat16>(float v, unsigned short& bits) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  bits = __bfloat16_as_ushort(h);
+  return __uint_as_float((uint32_t)bits << 16);
+}
+template <> __device__ __forceinline__ float round_to<__half>(float v, unsigned short& bits) {
+  const __half h = __float2half_rn(v);
+  bits = __half_as_ushort(h);
+  return __half2float(h);
+}
+
+// The accumulator is held TRANSPOSED: TMEM lane = output column (a row of W, the M operand), TMEM column = pair row
+// (columns 0-127: f1 rows -> x, 128-255: f2 rows -> y; [f1 tile; f2 tile] is one 256-row N operand).  One N=256 MMA per
+// K step moves 12 KB of operands per 128 tensor-core cycles (two N=128 MMAs would move 16 KB: shared-memory bound).
 template <typename T, int MEASURE>
 __global__ void __launch_bounds__(proj::THREADS, 1)
 project_kernel(const __grid_constant__ CUtensorMap tmap_f1, const __grid_constant__ CUtensorMap tmap_f2,
                const __grid_constant__ CUtensorMap tmap_w, const ProjParams p) {
   using namespace proj;
   constexpr bool SCORE = MEASURE != kNoScore;
+  constexpr bool NEED_COS = MEASURE == IA_COSINE;
   constexpr int AB_FORMAT = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  float* bias_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + kMaxH * 4);
+  float4* sums_s = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + SUMS_BYTES);
   uint64_t* full_bar = bars;                // [STAGES] TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;      // [STAGES] MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * STAGES;  // [2] MMA -> epilogue
@@ -99,12 +117,10 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_f1, const __grid_constan
     tma_prefetch_desc(&tmap_f2);
     tma_prefetch_desc(&tmap_w);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], EPI_WARPS); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, 512);
-  // bias (zero beyond h, so padded columns come out as tanh(0) = 0)
-  for (int i = threadIdx.x; i < p.n_ct * BN; i += THREADS) bias_s[i] = (p.bias != nullptr && i < p.h) ? __ldg(p.bias + i) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -124,9 +140,9 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_f1, const __grid_constan
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
             uint8_t* s0 = smem + stage * STAGE_BYTES;
-            tma_load_2d(s0, &tmap_f1, &full_bar[stage], kb * BK, rb * BM);
-            tma_load_2d(s0 + A_BYTES, &tmap_f2, &full_bar[stage], kb * BK, rb * BM);
-            tma_load_2d(s0 + 2 * A_BYTES, &tmap_w, &full_bar[stage], kb * BK, ct * BN);
+            tma_load_2d(s0, &tmap_w, &full_bar[stage], kb * BK, ct * BN);
+            tma_load_2d(s0 + W_BYTES, &tmap_f1, &full_bar[stage], kb * BK, rb * BM);
+            tma_load_2d(s0 + W_BYTES + A_BYTES, &tmap_f2, &full_bar[stage], kb * BK, rb * BM);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -135,29 +151,30 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_f1, const __grid_constan
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(BM, BN, AB_FORMAT);
+      constexpr uint32_t idesc = umma_idesc(BN, 2 * BM, AB_FORMAT);   // M = 128 output columns, N = 256 pair rows
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
+      long long w_epi = 0, w_tma = 0;
+      const long long t_begin = clock64();
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int part = item % p.parts;
         const int ct0 = part * p.cts_per_part, ct1 = min(ct0 + p.cts_per_part, p.n_ct);
         for (int ct = ct0; ct < ct1; ++ct) {
+          long long c0 = clock64();
           mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+          w_epi += clock64() - c0;
           tc_fence_after();
-          const uint32_t dx_tmem = tmem_base + acc * (2 * BN);
-          const uint32_t dy_tmem = dx_tmem + BN;
+          const uint32_t d_tmem = tmem_base + acc * (2 * BM);
           for (int kb = 0; kb < p.kblocks; ++kb) {
+            c0 = clock64();
             mbar_wait(&full_bar[stage], phase);
+            w_tma += clock64() - c0;
             tc_fence_after();
             const uint32_t s0 = smem_u32(smem + stage * STAGE_BYTES);
-            const uint64_t a1 = umma_smem_desc_sw128(s0);
-            const uint64_t a2 = umma_smem_desc_sw128(s0 + A_BYTES);
-            const uint64_t wd = umma_smem_desc_sw128(s0 + 2 * A_BYTES);
+            const uint64_t wd = umma_smem_desc_sw128(s0);
+            const uint64_t fd = umma_smem_desc_sw128(s0 + W_BYTES);
 #pragma unroll
-            for (int k4 = 0; k4 < BK / 16; ++k4) {
-              umma_f16(dx_tmem, a1 + 2 * k4, wd + 2 * k4, idesc, (kb | k4) != 0);
-              umma_f16(dy_tmem, a2 + 2 * k4, wd + 2 * k4, idesc, (kb | k4) != 0);
-            }
+            for (int k4 = 0; k4 < BK / 16; ++k4) umma_f16(d_tmem, wd + 2 * k4, fd + 2 * k4, idesc, (kb | k4) != 0);
             umma_commit(&empty_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -165,54 +182,98 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_f1, const __grid_constan
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }
+      if (p.stats != nullptr) {
+        atomicAdd(p.stats + 0, (unsigned long long)w_epi);
+        atomicAdd(p.stats + 1, (unsigned long long)w_tma);
+        atomicAdd(p.stats + 2, (unsigned long long)(clock64() - t_begin));
+      }
     }
   } else {
     // ------------------------------------------------------------------ epilogue: bias + tanh + round (+ row sums)
     const int e = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row_local = e * 32 + lane;
-    T* xo = reinterpret_cast<T*>(p.x);
-    T* yo = reinterpret_cast<T*>(p.y);
+    const int g0 = ((warp - 2) >> 2) * (BM / 32 / 2);   // this warp's half of the pair rows (TMEM columns)
+    unsigned short* xo = reinterpret_cast<unsigned short*>(p.x);
+    unsigned short* yo = reinterpret_cast<unsigned short*>(p.y);
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long w_mma = 0;
+    const long long t_begin = clock64();
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int rb = item / p.parts, part = item % p.parts;
       const int ct0 = part * p.cts_per_part, ct1 = min(ct0 + p.cts_per_part, p.n_ct);
-      const int64_t row = (int64_t)rb * BM + row_local;
-      const bool row_ok = row < p.n;
-      RowSums s{0.f, 0.f, 0.f, 0.f};
+      const int64_t row0 = (int64_t)rb * BM;
+      // lane l of this warp owns the sums of pair rows row0 + g*32 + l over the warp's columns of the item's tiles
+      float4* my_sums = sums_s + e * BM + lane;
+      if (SCORE) {
+#pragma unroll
+        for (int g = g0; g < g0 + BM / 32 / 2; ++g) my_sums[g * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       for (int ct = ct0; ct < ct1; ++ct) {
+        const int col = ct * BN + e * 32 + lane;      // output column of this thread == TMEM lane
+        const bool col_ok = col < p.h;
+        const float bias = (col_ok && p.bias != nullptr) ? __ldg(p.bias + col) : 0.f;
+        const long long c0 = clock64();
         mbar_wait(&tfull_bar[acc], acc_phase);
+        w_mma += clock64() - c0;
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + acc * (2 * BN);
+        const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + acc * (2 * BM);
 #pragma unroll 1
-        for (int g = 0; g < BN / 32; ++g) {
+        for (int g = g0; g < g0 + BM / 32 / 2; ++g) {
           uint32_t rx[32], ry[32];
           tmem_ld_32x32(taddr + g * 32, rx);
-          tmem_ld_32x32(taddr + BN + g * 32, ry);
+          tmem_ld_32x32(taddr + BM + g * 32, ry);
           tmem_ld_wait();
-          const int col0 = ct * BN + g * 32;
+          const int64_t r_base = row0 + g * 32;
+          // all 64 tanh chains first, branch-free (the scheduler interleaves them), then the stores
+          unsigned short bx[32], by[32];
+          float fx[32], fy[32];
 #pragma unroll
-          for (int c = 0; c < 32; c += 8) {
-            float fx[8], fy[8];
-            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col0 + c);
-            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + col0 + c + 4);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          for (int i = 0; i < 32; ++i) {
+            fx[i] = round_to<T>(tanh_f32(__uint_as_float(rx[i]) + bias), bx[i]);
+            fy[i] = round_to<T>(tanh_f32(__uint_as_float(ry[i]) + bias), by[i]);
+          }
+          // a warp writes 32 consecutive columns of one row per store: 64 contiguous bytes
+          const int rows_here = col_ok ? (int)min((int64_t)32, p.n - r_base) : 0;
+          if (xo != nullptr) {
+            unsigned short* px = xo + r_base * p.ldx + col;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              fx[j] = tanh_f32(__uint_as_float(rx[c + j]) + bb[j]);
-              fy[j] = tanh_f32(__uint_as_float(ry[c + j]) + bb[j]);
+            for (int i = 0; i < 32; ++i) {
+              if (i < rows_here) px[0] = bx[i];
+              px += p.ldx;
             }
-            const uint4 vx = pack8<T>(fx), vy = pack8<T>(fy);
-            const bool col_ok = col0 + c < p.h;   // h % 8 == 0: a chunk is entirely inside or outside
-            if (row_ok && col_ok) {
-              if (xo != nullptr) stg_stream(reinterpret_cast<uint4*>(xo + row * p.ldx + col0 + c), vx);
-              if (yo != nullptr) stg_stream(reinterpret_cast<uint4*>(yo + row * p.ldy + col0 + c), vy);
+          }
+          if (yo != nullptr) {
+            unsigned short* py = yo + r_base * p.ldy + col;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (i < rows_here) py[0] = by[i];
+              py += p.ldy;
             }
-            if (SCORE && col_ok) {
-              unpack<T>(vx, fx);   // score the values the embeddings hold after rounding, like the reference does
-              unpack<T>(vy, fy);
-              accumulate<MEASURE, false>(fx, fy, 8, s);
+          }
+          if (SCORE) {
+            // scored from the rounded values, like the reference scores the embeddings it returns; one butterfly
+            // transpose-reduce per kind of row sum, reusing the same 32 registers
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float t;
+              if (MEASURE == IA_INNER || MEASURE == IA_COSINE) t = fx[i] * fy[i];
+              else if (MEASURE == IA_L1) t = fabsf(fx[i] - fy[i] + kPdistEps);
+              else { const float dd = fx[i] - fy[i] + kPdistEps; t = dd * dd; }
+              v[i] = col_ok ? t : 0.f;
             }
+            float4 acc4 = my_sums[g * 32];
+            const float t0 = warp_transpose_sum(v, lane);
+            if (MEASURE == IA_INNER || MEASURE == IA_COSINE) acc4.x += t0; else acc4.w += t0;
+            if (NEED_COS) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = col_ok ? fx[i] * fx[i] : 0.f;
+              acc4.y += warp_transpose_sum(v, lane);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = col_ok ? fy[i] * fy[i] : 0.f;
+              acc4.z += warp_transpose_sum(v, lane);
+            }
+            my_sums[g * 32] = acc4;
           }
         }
         tc_fence_before();
@@ -220,7 +281,17 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_f1, const __grid_constan
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (SCORE && row_ok) p.sums[(size_t)part * p.n + row] = make_float4(s.xy, s.xx, s.yy, s.dist);
+      if (SCORE) {
+#pragma unroll
+        for (int g = g0; g < g0 + BM / 32 / 2; ++g) {
+          const int64_t r = row0 + g * 32 + lane;
+          if (r < p.n) p.sums[((size_t)part * 4 + e) * p.n + r] = my_sums[g * 32];
+        }
+      }
+    }
+    if (p.stats != nullptr && lane == 0) {
+      atomicAdd(p.stats + 3, (unsigned long long)w_mma);
+      atomicAdd(p.stats + 4, (unsigned long long)(clock64() - t_begin));
     }
   }
 
@@ -316,6 +387,16 @@ static int project_dispatch(int measure, const CUtensorMap& m1, const CUtensorMa
   return IA_ERR_INVALID;
 }
 
+static unsigned long long* g_proj_stats[16] = {nullptr};
+static unsigned long long* proj_stats_buffer() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (g_proj_stats[dev] == nullptr) {
+    if (cudaMalloc(&g_proj_stats[dev], 8 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+  }
+  return g_proj_stats[dev];
+}
+
 static int project_common(int measure, int dtype, const void* f1, const void* f2, int64_t ldf1, int64_t ldf2, int64_t n,
                           int64_t k_in, const void* w, int64_t ldw, const float* bias, int64_t h, void* x, void* y, int64_t ldx,
                           int64_t ldy, float4* sums, const ProjPlan& pl, cudaStream_t st) {
@@ -343,6 +424,12 @@ static int project_common(int measure, int dtype, const void* f1, const void* f2
   if ((rc = make_tmap(&mw, dtype, w, h, k_in, ldw, proj::BN)) != IA_OK) return rc;
   ProjParams p;
   p.n = n; p.h = (int)h; p.kblocks = pl.kblocks; p.n_rb = pl.n_rb; p.n_ct = pl.n_ct; p.parts = pl.parts;
+  {
+    const char* dbg = getenv("IA_PROJ_DEBUG");   // diagnostics only: 2 = collect cycle counters (ia_project_last_stats)
+    p.debug_flags = dbg ? atoi(dbg) : 0;
+    p.stats = (p.debug_flags & 2) ? proj_stats_buffer() : nullptr;
+    if (p.stats != nullptr) IA_CUDA_CHECK(cudaMemsetAsync(p.stats, 0, 8 * sizeof(unsigned long long), st));
+  }
   p.cts_per_part = pl.cts_per_part; p.bias = bias; p.x = x; p.y = y; p.ldx = ldx; p.ldy = ldy; p.sums = sums;
   return dtype == IA_BF16 ? project_dispatch<__nv_bfloat16>(measure, m1, m2, mw, p, pl.ctas, st)
                           : project_dispatch<__half>(measure, m1, m2, mw, p, pl.ctas, st);
@@ -365,10 +452,17 @@ int ia_project_tanh_fwd(int dtype, const void* f1, const void* f2, int64_t ldf1,
                         (cudaStream_t)stream);
 }
 
+int ia_project_last_stats(uint64_t* out8) {
+  unsigned long long* buf = proj_stats_buffer();
+  if (buf == nullptr || out8 == nullptr) { set_error("projection: no stats buffer"); return IA_ERR_INVALID; }
+  IA_CUDA_CHECK(cudaMemcpy(out8, buf, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return IA_OK;
+}
+
 size_t ia_project_score_workspace_bytes(int64_t n, int64_t k_in, int64_t h) {
   ProjPlan pl;
   if (make_plan(n, k_in, h, &pl) != IA_OK) return 0;
-  return (size_t)pl.parts * (size_t)n * sizeof(float4);
+  return (size_t)pl.parts * 4 * (size_t)n * sizeof(float4);
 }
 
 int ia_project_score_fwd(int measure, int dtype, const void* f1, const void* f2, int64_t ldf1, int64_t ldf2, int64_t n,
@@ -383,7 +477,7 @@ int ia_project_score_fwd(int measure, int dtype, const void* f1, const void* f2,
     return IA_ERR_INVALID;
   }
   if (sim == nullptr) { set_error("projection: sim must not be null"); return IA_ERR_INVALID; }
-  const size_t need = (size_t)pl.parts * (size_t)n * sizeof(float4);
+  const size_t need = (size_t)pl.parts * 4 * (size_t)n * sizeof(float4);
   if (workspace == nullptr || workspace_bytes < need || ((uintptr_t)workspace & 15)) {
     set_error("projection: workspace of %zu bytes (16-byte aligned) required, got %zu", need, workspace_bytes);
     return IA_ERR_INVALID;
@@ -395,10 +489,10 @@ int ia_project_score_fwd(int measure, int dtype, const void* f1, const void* f2,
   const unsigned blocks = (unsigned)((n + 255) / 256);
   const float4* sums = reinterpret_cast<const float4*>(workspace);
   switch (measure) {
-    case IA_INNER: project_score_finalize<IA_INNER><<<blocks, 256, 0, st>>>(sums, pl.parts, n, sim, probs, threshold, labels_out); break;
-    case IA_COSINE: project_score_finalize<IA_COSINE><<<blocks, 256, 0, st>>>(sums, pl.parts, n, sim, probs, threshold, labels_out); break;
-    case IA_L1: project_score_finalize<IA_L1><<<blocks, 256, 0, st>>>(sums, pl.parts, n, sim, probs, threshold, labels_out); break;
-    default: project_score_finalize<IA_L2><<<blocks, 256, 0, st>>>(sums, pl.parts, n, sim, probs, threshold, labels_out); break;
+    case IA_INNER: project_score_finalize<IA_INNER><<<blocks, 256, 0, st>>>(sums, pl.parts * 4, n, sim, probs, threshold, labels_out); break;
+    case IA_COSINE: project_score_finalize<IA_COSINE><<<blocks, 256, 0, st>>>(sums, pl.parts * 4, n, sim, probs, threshold, labels_out); break;
+    case IA_L1: project_score_finalize<IA_L1><<<blocks, 256, 0, st>>>(sums, pl.parts * 4, n, sim, probs, threshold, labels_out); break;
+    default: project_score_finalize<IA_L2><<<blocks, 256, 0, st>>>(sums, pl.parts * 4, n, sim, probs, threshold, labels_out); break;
   }
   IA_LAUNCH_CHECK();
   return IA_OK;
