@@ -210,6 +210,40 @@ int ia_pair_score_loss_host(int measure, int loss, float margin, int reduction, 
                             const void* x, const void* y, const int64_t* labels, int64_t n, int64_t d,
                             float* loss_out, void* dx, void* dy, int device);
 
+/* ---- dissimilarity ranking with explicit eps / squaring -----------------------
+ * The l1 / l2 all-pairs kernel with the two knobs that separate nn.PairwiseDistance (eps = 1e-6 added to
+ * every difference, base.py:59-62) from torchkge's plain norms (torchkge/torchkge/utils/dissimilarities.py:11-25:
+ * l1 = ||a-b||_1, l2 = ||a-b||_2^2; eps = 0, squared = 1), so that candidate ranking for link prediction
+ * (torchkge/torchkge/inference.py:216-246: scores = -dissimilarity(h + r, candidates), sort descending,
+ * top_k) runs through the catalog: keys hold the k SMALLEST distances, ties -> lower row.
+ * p_norm is 1 or 2; `squared` only matters for p_norm = 2. */
+int ia_catalog_topk_dissimilarity(ia_catalog* cat, int p_norm, float eps, int squared, const void* queries,
+                                  int64_t q, int64_t ldq, int k, uint64_t* keys_out, ia_stream_t stream);
+
+/* ---- binary catalog files ---------------------------------------------------
+ * Replaces the embedding JSONL of finetune_text.py:784-792 (one pair per line, embeddings as
+ * stringified float lists, read back with eval at model_ensemble.py:112) as the input of retrieval:
+ * a 64-byte header, the row-major [rows, dim] matrix at offset 4096 and an optional id table
+ * (uint64 offsets[rows+1] + UTF-8 bytes).  Host-side functions; only _upload touches the device. */
+typedef struct ia_catalog_file ia_catalog_file;
+/* data: rows x dim elements already in `dtype`; ids: rows C strings or NULL. */
+int ia_catalog_file_write(const char* path, int dtype, const void* data, int64_t rows, int64_t dim,
+                          const char* const* ids);
+int ia_catalog_file_open(const char* path, ia_catalog_file** out);        /* mmap, validates the layout */
+void ia_catalog_file_close(ia_catalog_file* f);
+int ia_catalog_file_info(const ia_catalog_file* f, int* dtype, int64_t* rows, int64_t* dim, int* has_ids);
+const void* ia_catalog_file_data(const ia_catalog_file* f);               /* the mapped matrix */
+const char* ia_catalog_file_id(const ia_catalog_file* f, int64_t row, int64_t* len);   /* not NUL-terminated */
+/* rows [row_begin, row_end) -> device_dst (row-major, ld = dim): a rank uploads its shard_bounds() slice.
+ * Double-buffered pinned staging; synchronises `stream` before returning. */
+int ia_catalog_file_upload(const ia_catalog_file* f, int64_t row_begin, int64_t row_end, void* device_dst,
+                           ia_stream_t stream);
+/* Native converter: reference JSONL -> catalog file.  side 0 = src_item_*, 1 = tgt_item_*, 2 = both;
+ * an item id is stored once (first occurrence).  Values are parsed with strtof (bit-exact float32 of
+ * what the reference printed) and rounded to `dtype` to nearest even. */
+int ia_embedding_jsonl_to_catalog(const char* jsonl_path, const char* out_path, int dtype, int side,
+                                  int64_t* rows_out, int64_t* dim_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,340 @@
+// Binary catalog files: the [C, D] embedding matrix + an item-id table, so that retrieval over 10^8 rows
+// starts from one mmap instead of parsing text.  Replaces the embedding JSONL the reference writes
+// (finetune_text.py:784-792: one pair per line, each embedding a stringified float list) and reads back with `eval`
+// (model_ensemble.py:112).  Host-side C++ only; the one device interaction is the chunked upload.
+//
+// Layout (little-endian):
+//   [0, 64)                     header: magic "IACATLG1", version, dtype, rows, dim, data_offset, ids_offset, ids_bytes
+//   [data_offset, +rows*dim*e)  row-major matrix, data_offset = 4096 (page aligned: the mmap'ed rows are 16-byte aligned)
+//   [ids_offset, +ids_bytes)    optional: uint64 offsets[rows + 1], then the UTF-8 ids back to back
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cerrno>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ia {
+namespace {
+
+constexpr char kMagic[8] = {'I', 'A', 'C', 'A', 'T', 'L', 'G', '1'};
+constexpr uint64_t kDataOffset = 4096;
+
+struct FileHeader {
+  char magic[8];
+  uint32_t version;
+  uint32_t dtype;
+  uint64_t rows, dim;
+  uint64_t data_offset, ids_offset, ids_bytes;
+  uint64_t reserved;
+};
+static_assert(sizeof(FileHeader) == 64, "header is 64 bytes");
+
+size_t elem_bytes(int dtype) { return dtype == IA_F32 ? 4 : 2; }
+
+// float -> bf16 / fp16 bits, round to nearest even (what torch's .to(dtype) does)
+uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN stays NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+uint16_t f32_to_f16(float f) {
+  const __half h = __float2half_rn(f);   // host path of cuda_fp16.h: IEEE round to nearest even
+  uint16_t b;
+  memcpy(&b, &h, 2);
+  return b;
+}
+
+int write_all(int fd, const void* buf, size_t n) {
+  const char* p = static_cast<const char*>(buf);
+  while (n > 0) {
+    const ssize_t w = write(fd, p, n);
+    if (w < 0) { if (errno == EINTR) continue; return -1; }
+    p += w; n -= (size_t)w;
+  }
+  return 0;
+}
+
+// Streams a catalog file: header placeholder, rows appended one at a time, ids gathered in memory, finish() patches the header.
+struct Writer {
+  int fd = -1;
+  int dtype = IA_BF16;
+  uint64_t rows = 0, dim = 0;
+  std::vector<uint64_t> id_off;
+  std::string id_blob;
+  std::vector<uint8_t> rowbuf;
+  bool with_ids = false;
+
+  int open_file(const char* path, int dt, bool ids) {
+    fd = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) { set_error("cannot create %s: %s", path, strerror(errno)); return IA_ERR_INVALID; }
+    dtype = dt; with_ids = ids;
+    std::vector<uint8_t> zero(kDataOffset, 0);
+    if (write_all(fd, zero.data(), zero.size()) != 0) { set_error("write failed: %s", strerror(errno)); return IA_ERR_CUDA; }
+    id_off.push_back(0);
+    return IA_OK;
+  }
+  int add_row(const float* v, uint64_t d, const char* id, size_t id_len) {
+    if (rows == 0) { dim = d; rowbuf.resize(d * elem_bytes(dtype)); }
+    if (d != dim) { set_error("row %llu has %llu values, expected %llu", (unsigned long long)rows, (unsigned long long)d, (unsigned long long)dim); return IA_ERR_INVALID; }
+    if (dtype == IA_F32) memcpy(rowbuf.data(), v, d * 4);
+    else {
+      uint16_t* o = reinterpret_cast<uint16_t*>(rowbuf.data());
+      for (uint64_t i = 0; i < d; ++i) o[i] = dtype == IA_BF16 ? f32_to_bf16(v[i]) : f32_to_f16(v[i]);
+    }
+    if (write_all(fd, rowbuf.data(), rowbuf.size()) != 0) { set_error("write failed: %s", strerror(errno)); return IA_ERR_CUDA; }
+    if (with_ids) { id_blob.append(id, id_len); id_off.push_back(id_blob.size()); }
+    ++rows;
+    return IA_OK;
+  }
+  int add_raw_rows(const void* data, uint64_t n, uint64_t d) {   // already in the file dtype
+    if (rows == 0) dim = d;
+    if (write_all(fd, data, n * d * elem_bytes(dtype)) != 0) { set_error("write failed: %s", strerror(errno)); return IA_ERR_CUDA; }
+    rows += n;
+    return IA_OK;
+  }
+  int finish() {
+    FileHeader h{};
+    memcpy(h.magic, kMagic, 8);
+    h.version = 1; h.dtype = (uint32_t)dtype; h.rows = rows; h.dim = dim; h.data_offset = kDataOffset;
+    const uint64_t data_end = kDataOffset + rows * dim * elem_bytes(dtype);
+    if (with_ids) {
+      const uint64_t pad = (8 - data_end % 8) % 8;
+      const char zeros[8] = {0};
+      if (pad && write_all(fd, zeros, pad) != 0) { set_error("write failed: %s", strerror(errno)); return IA_ERR_CUDA; }
+      h.ids_offset = data_end + pad;
+      h.ids_bytes = id_off.size() * 8 + id_blob.size();
+      if (write_all(fd, id_off.data(), id_off.size() * 8) != 0 || write_all(fd, id_blob.data(), id_blob.size()) != 0) {
+        set_error("write failed: %s", strerror(errno));
+        return IA_ERR_CUDA;
+      }
+    }
+    if (pwrite(fd, &h, sizeof(h), 0) != (ssize_t)sizeof(h)) { set_error("header write failed: %s", strerror(errno)); return IA_ERR_CUDA; }
+    return IA_OK;
+  }
+  ~Writer() { if (fd >= 0) ::close(fd); }
+};
+
+// value of a JSON string member `"key": "..."` on one line (the reference writes flat objects with json.dumps, so a key
+// cannot occur inside another value except as escaped text, which the leading quote test excludes)
+bool find_string_member(const char* line, size_t len, const char* key, const char** val, size_t* val_len) {
+  const size_t klen = strlen(key);
+  for (size_t i = 0; i + klen + 2 < len; ++i) {
+    if (line[i] != '"' || (i > 0 && line[i - 1] == '\\')) continue;
+    if (memcmp(line + i + 1, key, klen) != 0 || line[i + 1 + klen] != '"') continue;
+    size_t j = i + klen + 2;
+    while (j < len && (line[j] == ' ' || line[j] == ':')) ++j;
+    if (j >= len || line[j] != '"') return false;
+    const size_t start = ++j;
+    while (j < len && !(line[j] == '"' && line[j - 1] != '\\')) ++j;
+    if (j >= len) return false;
+    *val = line + start; *val_len = j - start;
+    return true;
+  }
+  return false;
+}
+
+// "[0.1,-2.5e-3, ...]" -> floats.  strtof is correctly rounded, so the float32 the reference printed (repr of numpy
+// float32 = shortest round-trip decimal) comes back bit for bit.
+bool parse_float_list(const char* s, size_t len, std::vector<float>* out) {
+  out->clear();
+  std::string tmp(s, len);   // NUL-terminated copy for strtof
+  const char* p = tmp.c_str();
+  while (*p == ' ' || *p == '[') ++p;
+  while (*p && *p != ']') {
+    char* end = nullptr;
+    const float v = strtof(p, &end);
+    if (end == p) return false;
+    out->push_back(v);
+    p = end;
+    while (*p == ' ' || *p == ',') ++p;
+  }
+  return true;
+}
+
+}  // namespace
+}  // namespace ia
+
+using namespace ia;
+
+struct ia_catalog_file {
+  int fd;
+  void* map;
+  size_t map_bytes;
+  FileHeader hdr;
+  const uint64_t* id_off;
+  const char* id_blob;
+};
+
+extern "C" {
+
+int ia_catalog_file_write(const char* path, int dtype, const void* data, int64_t rows, int64_t dim, const char* const* ids) {
+  if (path == nullptr || (rows > 0 && data == nullptr) || rows < 0 || dim <= 0) { set_error("catalog file: bad arguments"); return IA_ERR_INVALID; }
+  if (dtype != IA_F32 && dtype != IA_BF16 && dtype != IA_F16) { set_error("catalog file: unsupported dtype %d", dtype); return IA_ERR_UNSUPPORTED; }
+  Writer w;
+  int rc = w.open_file(path, dtype, ids != nullptr);
+  if (rc != IA_OK) return rc;
+  w.dim = (uint64_t)dim;
+  if ((rc = w.add_raw_rows(data, (uint64_t)rows, (uint64_t)dim)) != IA_OK) return rc;
+  if (ids != nullptr)
+    for (int64_t i = 0; i < rows; ++i) { w.id_blob.append(ids[i] ? ids[i] : ""); w.id_off.push_back(w.id_blob.size()); }
+  return w.finish();
+}
+
+int ia_catalog_file_open(const char* path, ia_catalog_file** out) {
+  if (path == nullptr || out == nullptr) { set_error("catalog file: bad arguments"); return IA_ERR_INVALID; }
+  const int fd = ::open(path, O_RDONLY);
+  if (fd < 0) { set_error("cannot open %s: %s", path, strerror(errno)); return IA_ERR_INVALID; }
+  struct stat st;
+  if (fstat(fd, &st) != 0 || (size_t)st.st_size < sizeof(FileHeader)) { ::close(fd); set_error("%s: not a catalog file (too short)", path); return IA_ERR_INVALID; }
+  void* map = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_SHARED, fd, 0);
+  if (map == MAP_FAILED) { ::close(fd); set_error("mmap of %s failed: %s", path, strerror(errno)); return IA_ERR_CUDA; }
+  ia_catalog_file* f = new ia_catalog_file{fd, map, (size_t)st.st_size, {}, nullptr, nullptr};
+  memcpy(&f->hdr, map, sizeof(FileHeader));
+  const FileHeader& h = f->hdr;
+  const bool dtype_ok = h.dtype == IA_F32 || h.dtype == IA_BF16 || h.dtype == IA_F16;
+  const uint64_t data_bytes = dtype_ok ? h.rows * h.dim * elem_bytes((int)h.dtype) : 0;
+  bool ok = memcmp(h.magic, kMagic, 8) == 0 && h.version == 1 && dtype_ok && h.dim > 0 && h.data_offset >= sizeof(FileHeader) &&
+            h.data_offset % 16 == 0 && h.data_offset + data_bytes <= (uint64_t)st.st_size;
+  if (ok && h.ids_offset != 0) {
+    ok = h.ids_offset % 8 == 0 && h.ids_offset >= h.data_offset + data_bytes && h.ids_offset + h.ids_bytes <= (uint64_t)st.st_size &&
+         h.ids_bytes >= (h.rows + 1) * 8;
+    if (ok) {
+      f->id_off = reinterpret_cast<const uint64_t*>(static_cast<const char*>(map) + h.ids_offset);
+      f->id_blob = reinterpret_cast<const char*>(f->id_off + h.rows + 1);
+      ok = f->id_off[0] == 0 && (h.rows + 1) * 8 + f->id_off[h.rows] == h.ids_bytes;
+    }
+  }
+  if (!ok) {
+    munmap(map, (size_t)st.st_size); ::close(fd); delete f;
+    set_error("%s: not a valid catalog file (bad magic, version, dtype or section bounds)", path);
+    return IA_ERR_INVALID;
+  }
+  *out = f;
+  return IA_OK;
+}
+
+void ia_catalog_file_close(ia_catalog_file* f) {
+  if (f == nullptr) return;
+  munmap(f->map, f->map_bytes);
+  ::close(f->fd);
+  delete f;
+}
+
+int ia_catalog_file_info(const ia_catalog_file* f, int* dtype, int64_t* rows, int64_t* dim, int* has_ids) {
+  if (f == nullptr) { set_error("catalog file: null handle"); return IA_ERR_INVALID; }
+  if (dtype) *dtype = (int)f->hdr.dtype;
+  if (rows) *rows = (int64_t)f->hdr.rows;
+  if (dim) *dim = (int64_t)f->hdr.dim;
+  if (has_ids) *has_ids = f->id_off != nullptr;
+  return IA_OK;
+}
+
+const void* ia_catalog_file_data(const ia_catalog_file* f) {
+  return f == nullptr ? nullptr : static_cast<const char*>(f->map) + f->hdr.data_offset;
+}
+
+const char* ia_catalog_file_id(const ia_catalog_file* f, int64_t row, int64_t* len) {
+  if (f == nullptr || f->id_off == nullptr || row < 0 || (uint64_t)row >= f->hdr.rows) { if (len) *len = 0; return nullptr; }
+  if (len) *len = (int64_t)(f->id_off[row + 1] - f->id_off[row]);
+  return f->id_blob + f->id_off[row];
+}
+
+// rows [row_begin, row_end) -> device memory (row-major, ld = dim), through two pinned staging buffers so that the
+// page-cache read of chunk i+1 overlaps the DMA of chunk i.  Synchronises the stream before returning.
+int ia_catalog_file_upload(const ia_catalog_file* f, int64_t row_begin, int64_t row_end, void* device_dst, ia_stream_t stream) {
+  if (f == nullptr || device_dst == nullptr || row_begin < 0 || row_end < row_begin || (uint64_t)row_end > f->hdr.rows) {
+    set_error("catalog upload: bad arguments");
+    return IA_ERR_INVALID;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t row_bytes = f->hdr.dim * elem_bytes((int)f->hdr.dtype);
+  const size_t total = (size_t)(row_end - row_begin) * row_bytes;
+  const char* src = static_cast<const char*>(ia_catalog_file_data(f)) + (size_t)row_begin * row_bytes;
+  const size_t chunk = 32u << 20;
+  void* stage[2] = {nullptr, nullptr};
+  cudaEvent_t done[2];
+  IA_CUDA_CHECK(cudaMallocHost(&stage[0], chunk));
+  if (cudaMallocHost(&stage[1], chunk) != cudaSuccess) { cudaFreeHost(stage[0]); set_error("pinned staging allocation failed"); return IA_ERR_CUDA; }
+  cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming);
+  int rc = IA_OK;
+  int b = 0;
+  for (size_t off = 0; off < total; off += chunk, b ^= 1) {
+    const size_t n = total - off < chunk ? total - off : chunk;
+    if (off >= 2 * chunk && cudaEventSynchronize(done[b]) != cudaSuccess) { rc = IA_ERR_CUDA; break; }   // staging buffer free again
+    memcpy(stage[b], src + off, n);
+    if (cudaMemcpyAsync(static_cast<char*>(device_dst) + off, stage[b], n, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaEventRecord(done[b], s) != cudaSuccess) { rc = IA_ERR_CUDA; break; }
+  }
+  if (cudaStreamSynchronize(s) != cudaSuccess) rc = IA_ERR_CUDA;
+  if (rc != IA_OK) set_error("catalog upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+  cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
+  cudaFreeHost(stage[0]); cudaFreeHost(stage[1]);
+  return rc;
+}
+
+// Reference embedding JSONL (finetune_text.py:784-792) -> catalog file.  side: 0 = src_item_*, 1 = tgt_item_*, 2 = both.
+// An item that occurs in several pairs is stored once (first occurrence wins, like a dict built in file order).
+int ia_embedding_jsonl_to_catalog(const char* jsonl_path, const char* out_path, int dtype, int side, int64_t* rows_out,
+                                  int64_t* dim_out) {
+  if (jsonl_path == nullptr || out_path == nullptr || side < 0 || side > 2) { set_error("jsonl: bad arguments"); return IA_ERR_INVALID; }
+  if (dtype != IA_F32 && dtype != IA_BF16 && dtype != IA_F16) { set_error("jsonl: unsupported dtype %d", dtype); return IA_ERR_UNSUPPORTED; }
+  FILE* in = fopen(jsonl_path, "r");
+  if (in == nullptr) { set_error("cannot open %s: %s", jsonl_path, strerror(errno)); return IA_ERR_INVALID; }
+  Writer w;
+  int rc = w.open_file(out_path, dtype, true);
+  if (rc != IA_OK) { fclose(in); return rc; }
+  std::unordered_map<std::string, uint64_t> seen;
+  std::vector<float> vals;
+  char* line = nullptr;
+  size_t cap = 0;
+  ssize_t len;
+  int64_t line_no = 0;
+  static const char* kId[2] = {"src_item_id", "tgt_item_id"};
+  static const char* kEmb[2] = {"src_item_emb", "tgt_item_emb"};
+  while (rc == IA_OK && (len = getline(&line, &cap, in)) >= 0) {
+    ++line_no;
+    bool blank = true;
+    for (ssize_t i = 0; i < len; ++i) if (line[i] != ' ' && line[i] != '\n' && line[i] != '\r' && line[i] != '\t') { blank = false; break; }
+    if (blank) continue;
+    for (int sd = 0; sd < 2 && rc == IA_OK; ++sd) {
+      if (side != 2 && side != sd) continue;
+      const char *id, *emb;
+      size_t id_len, emb_len;
+      if (!find_string_member(line, (size_t)len, kId[sd], &id, &id_len) || !find_string_member(line, (size_t)len, kEmb[sd], &emb, &emb_len)) {
+        set_error("%s:%lld: missing %s / %s", jsonl_path, (long long)line_no, kId[sd], kEmb[sd]);
+        rc = IA_ERR_INVALID;
+        break;
+      }
+      std::string key(id, id_len);
+      if (seen.count(key)) continue;
+      if (!parse_float_list(emb, emb_len, &vals) || vals.empty()) {
+        set_error("%s:%lld: %s is not a float list", jsonl_path, (long long)line_no, kEmb[sd]);
+        rc = IA_ERR_INVALID;
+        break;
+      }
+      seen.emplace(std::move(key), w.rows);
+      rc = w.add_row(vals.data(), vals.size(), id, id_len);
+    }
+  }
+  free(line);
+  fclose(in);
+  if (rc != IA_OK) return rc;
+  if ((rc = w.finish()) != IA_OK) return rc;
+  if (rows_out) *rows_out = (int64_t)w.rows;
+  if (dim_out) *dim_out = (int64_t)w.dim;
+  return IA_OK;
+}
+
+}  // extern "C"

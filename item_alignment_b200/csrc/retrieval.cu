@@ -38,6 +38,8 @@ struct RetrParams {
   uint32_t* tau_global; // [n_qt*BM] best published k-th goodness per query (0 = none)
   uint32_t* done;       // [n_items*4] set when a warp's quarter of an item's lists is final
   unsigned long long* stats;  // [8] appends, compactions, rare groups, rare blocks (telemetry)
+  float dist_eps;       // l1 / l2: eps added to every difference (nn.PairwiseDistance 1e-6; 0 for plain norms)
+  int dist_squared;     // l2: rank and report the squared distance (torchkge l2_dissimilarity)
   uint32_t row_base;    // global row id of catalog row 0 (shard offset)
   int flags;            // tuning switches for in-run A/B measurements (env IA_RETR_FLAGS, default 14): bit1 early tau
                         // load, bit2 finished-split bound, bit3 paced merges (<= 2 lanes per tile after release)
@@ -415,6 +417,7 @@ retrieve_simt_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ty = tid >> 4, tx = tid & 15;
   const int n_items = p.n_qt * p.n_splits;
+  const float eps = p.dist_eps;
 
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int qt = item % p.n_qt, split = item / p.n_qt;
@@ -453,7 +456,7 @@ retrieve_simt_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__
         for (int idx = tid; idx < BN * BK; idx += THREADS) {
           const int row = idx / BK, kk = idx % BK;
           // padded k / rows: c = eps so that (0 - eps) + eps == 0 adds nothing to an l1/l2 distance
-          float v = DIST ? kPdistEps : 0.f;
+          float v = DIST ? p.dist_eps : 0.f;
           if (j0 + row < p.c_rows && k0 + kk < p.d) v = to_float<T>(cat[(j0 + row) * ldc + k0 + kk]);
           Cs[kk * (BN + 1) + row] = v;
         }
@@ -471,7 +474,7 @@ retrieve_simt_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__
             for (int j = 0; j < 8; ++j) {
               if (DESC) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
               else {
-                const float dd = a[i] - b[j] + kPdistEps;   // nn.PairwiseDistance: eps added to the difference
+                const float dd = a[i] - b[j] + eps;   // nn.PairwiseDistance: eps added to the difference
                 if (MEASURE == IA_L1) acc[i][j] += fabsf(dd);
                 else acc[i][j] = fmaf(dd, dd, acc[i][j]);
               }
@@ -496,7 +499,7 @@ retrieve_simt_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__
         for (int c = 0; c < BN; ++c) {
           float s = Ss[tid * (BN + 1) + c];
           const int64_t j = j0 + c;
-          if (MEASURE == IA_L2) s = sqrtf(s);
+          if (MEASURE == IA_L2 && !p.dist_squared) s = sqrtf(s);
           if (MEASURE == IA_COSINE) s = (s * ((j < p.c_rows) ? __ldg(p.cinv + j) : 0.f)) * qinv;
           const bool pass = DESC ? (s >= thr_f) : (s <= thr_f);
           if (q_ok && j < p.c_rows && pass) {
@@ -734,8 +737,8 @@ int ia_catalog_topk(ia_catalog* cat, int measure, const void* queries, int64_t q
   return ia_catalog_topk_seeded(cat, measure, queries, q, ldq, k, nullptr, keys_out, stream);
 }
 
-int ia_catalog_topk_seeded(ia_catalog* cat, int measure, const void* queries, int64_t q, int64_t ldq, int k,
-                           const int64_t* tau_init, uint64_t* keys_out, ia_stream_t stream) {
+static int catalog_topk_impl(ia_catalog* cat, int measure, float dist_eps, int dist_squared, const void* queries, int64_t q,
+                             int64_t ldq, int k, const int64_t* tau_init, uint64_t* keys_out, ia_stream_t stream) {
   if (cat == nullptr || queries == nullptr || keys_out == nullptr || q < 0 || ldq < cat->d) { set_error("bad arguments"); return IA_ERR_INVALID; }
   if (measure < IA_INNER || measure > IA_L2) { set_error("Unsupported similarty measure: %d", measure); return IA_ERR_INVALID; }
   if (k < 1 || k > IA_MAX_K) { set_error("k must be in [1, %d]", IA_MAX_K); return IA_ERR_INVALID; }
@@ -754,6 +757,7 @@ int ia_catalog_topk_seeded(ia_catalog* cat, int measure, const void* queries, in
   p.n_tiles = (int)((cat->c + BN - 1) / BN);
   p.kblocks = (int)((cat->d + tc::BK - 1) / tc::BK);
   p.row_base = cat->row_base;
+  p.dist_eps = dist_eps; p.dist_squared = dist_squared;
   p.flags = 14;
   if (const char* f = getenv("IA_RETR_FLAGS")) p.flags = atoi(f);
   const int sms = sm_count();
@@ -830,6 +834,19 @@ int ia_catalog_topk_seeded(ia_catalog* cat, int measure, const void* queries, in
                                            keys_out);
   IA_LAUNCH_CHECK();
   return IA_OK;
+}
+
+int ia_catalog_topk_seeded(ia_catalog* cat, int measure, const void* queries, int64_t q, int64_t ldq, int k,
+                           const int64_t* tau_init, uint64_t* keys_out, ia_stream_t stream) {
+  return catalog_topk_impl(cat, measure, kPdistEps, 0, queries, q, ldq, k, tau_init, keys_out, stream);
+}
+
+int ia_catalog_topk_dissimilarity(ia_catalog* cat, int p_norm, float eps, int squared, const void* queries, int64_t q,
+                                  int64_t ldq, int k, uint64_t* keys_out, ia_stream_t stream) {
+  if (p_norm != 1 && p_norm != 2) { set_error("dissimilarity: p must be 1 or 2"); return IA_ERR_INVALID; }
+  if (!(eps >= 0.f)) { set_error("dissimilarity: eps must be >= 0"); return IA_ERR_INVALID; }
+  return catalog_topk_impl(cat, p_norm == 1 ? IA_L1 : IA_L2, eps, (p_norm == 2 && squared) ? 1 : 0, queries, q, ldq, k, nullptr,
+                           keys_out, stream);
 }
 
 int ia_catalog_last_plan(ia_catalog* cat, int* splits, int* tiles_per_split) {

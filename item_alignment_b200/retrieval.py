@@ -87,6 +87,24 @@ class CatalogIndex:
         """(scores [Q,k] fp32, rows [Q,k] int64 global ids), best first; -1 / +-inf where fewer than k rows exist."""
         return unpack_keys(self.topk_keys(queries, k, measure), measure)
 
+    def topk_dissimilarity(self, queries, k, p=2, eps=0.0, squared=None):
+        """The k SMALLEST l1 / l2 dissimilarities per query with explicit eps / squaring: (dist [Q,k] ascending, rows).
+        Defaults are torchkge's plain norms (torchkge/utils/dissimilarities.py:11-25: l1, l2 squared);
+        eps=1e-6, squared=False is nn.PairwiseDistance."""
+        if p not in (1, 2):
+            raise ValueError("p must be 1 or 2")
+        squared = (p == 2) if squared is None else bool(squared)
+        if not queries.is_cuda or queries.dim() != 2 or queries.shape[1] != self.catalog.shape[1]:
+            raise ValueError("queries must be a [Q, D] CUDA tensor with the catalog's D")
+        queries = queries.to(self.catalog.dtype)
+        if queries.stride(1) != 1:
+            queries = queries.contiguous()
+        keys = torch.empty((queries.shape[0], k), dtype=torch.int64, device=queries.device)
+        with torch.cuda.device(queries.device):
+            check(lib().ia_catalog_topk_dissimilarity(self._h, int(p), float(eps), int(squared), queries.data_ptr(),
+                                                      queries.shape[0], _ld(queries), int(k), keys.data_ptr(), _stream()))
+        return unpack_keys(keys, "l2")
+
     def last_stats(self):
         """Telemetry of the last topk call (synchronises): appended keys, merges, rare groups, rare blocks."""
         out = (ctypes.c_uint64 * 8)()
@@ -210,3 +228,26 @@ class ShardedCatalogIndex:
 
     def topk(self, queries, k, measure="cosine"):
         return unpack_keys(self.topk_keys(queries, k, measure), measure)
+
+
+def rank_entities(ent_emb, rel_emb, known_entities, known_relations, top_k=1, missing="tails", dissimilarity_type="L2",
+                  index=None):
+    """TransE candidate ranking of torchkge's EntityInference (torchkge/torchkge/inference.py:216-246) through the
+    catalog kernels: scores = -dissimilarity(h + r, c) (tails) or -dissimilarity(c + r, t) (heads) for every entity c,
+    sorted descending, top_k.  Returns (predictions [n, top_k] int64, scores [n, top_k] fp32) like the reference's
+    `.predictions` / `.scores`.  The all-candidates score matrix [n, n_ent] is never built."""
+    if missing not in ("heads", "tails"):
+        raise ValueError("missing entity should either be 'heads' or 'tails'")
+    if dissimilarity_type not in ("L1", "L2"):
+        raise ValueError("dissimilarity_type must be 'L1' or 'L2'")
+    e = ent_emb[known_entities]
+    r = rel_emb[known_relations]
+    queries = e + r if missing == "tails" else e - r      # ||c + r - t|| = ||c - (t - r)||
+    own = index is None
+    index = CatalogIndex(ent_emb) if own else index
+    try:
+        dist, rows = index.topk_dissimilarity(queries, top_k, p=1 if dissimilarity_type == "L1" else 2)
+    finally:
+        if own:
+            index.close()
+    return rows, -dist

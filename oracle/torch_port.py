@@ -10,6 +10,7 @@ by the real reference modules (tests/golden/make_golden.py).
 bf16/fp16 policy (SURVEY 7 "bf16 oracle"): the oracle always runs on ``x.float()`` of
 the already-quantised inputs and emits fp32.
 """
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -268,3 +269,61 @@ def gcn_pair_loop(measure, node_embeddings, pairs, loss_type=None, margin=1.0):
     if loss is not None:
         loss = loss / len(pairs)
     return torch.cat(sims), torch.cat(probs_all), loss
+
+
+# ----------------------------------------------------------------------------------------------
+# Rank-4 "next" row: the embedding JSONL wire format and torchkge-style candidate ranking
+def embedding_jsonl_record(src_item_id, tgt_item_id, src_embed, tgt_embed, threshold):
+    """One line of the reference's embedding dump, finetune_text.py:784-792: each embedding is
+    ','.join(str(v) for v in ndarray) wrapped in brackets, the record goes through json.dumps."""
+    import json
+    src_item_emb = ','.join([str(emb) for emb in src_embed])
+    tgt_item_emb = ','.join([str(emb) for emb in tgt_embed])
+    rd = {"src_item_id": src_item_id, "src_item_emb": f"[{src_item_emb}]",
+          "tgt_item_id": tgt_item_id, "tgt_item_emb": f"[{tgt_item_emb}]", "threshold": threshold}
+    return json.dumps(rd) + "\n"
+
+
+def read_embedding_jsonl(path, side="both"):
+    """What a consumer of that file sees: json.loads per line and the float list evaluated like
+    model_ensemble.py:112 does (`eval(d['tgt_item_emb'])`; literal_eval here, same value for a list of
+    floats), first occurrence of an item id kept.  Returns (ids, float32 matrix)."""
+    import ast
+    import json
+    ids, rows, seen = [], [], set()
+    with open(path, "r", encoding="utf-8") as r:
+        for line in r:
+            if not line.strip():
+                continue
+            d = json.loads(line.strip())
+            for s in (("src", "tgt") if side == "both" else (side,)):
+                key = d[f"{s}_item_id"]
+                if key in seen:
+                    continue
+                seen.add(key)
+                ids.append(key)
+                rows.append(np.asarray(ast.literal_eval(d[f"{s}_item_emb"]), dtype=np.float64).astype(np.float32))
+    return ids, np.stack(rows)
+
+
+def kg_dissimilarity(kind, a, b):
+    """torchkge/torchkge/utils/dissimilarities.py:11-25: L1 = ||a-b||_1, L2 = ||a-b||_2 ** 2."""
+    if kind == "L1":
+        return (a - b).norm(p=1, dim=-1)
+    return (a - b).norm(p=2, dim=-1) ** 2
+
+
+def kg_rank_entities(ent_emb, rel_emb, known_entities, known_relations, top_k, missing="tails", kind="L2"):
+    """EntityInference.evaluate for a TransE model, torchkge/torchkge/inference.py:216-246 with
+    TranslationModel.inference_scoring_function (models/interfaces.py:240-260): tails:
+    -dissimilarity((h + r)[:, None, :], candidates); heads: -dissimilarity(candidates + r[:, None, :], t[:, None, :]);
+    `scores.sort(descending=True)` (made stable here so ties are defined: lower entity index first), top_k."""
+    cand = ent_emb.float()[None, :, :]
+    e = ent_emb.float()[known_entities]
+    r = rel_emb.float()[known_relations]
+    if missing == "tails":
+        scores = -kg_dissimilarity(kind, (e + r)[:, None, :], cand)
+    else:
+        scores = -kg_dissimilarity(kind, cand + r[:, None, :], e[:, None, :])
+    s, idx = torch.sort(scores, dim=1, descending=True, stable=True)
+    return idx[:, :top_k], s[:, :top_k], scores

@@ -13,6 +13,7 @@ Files written
   pair_golden.npz        measure x loss x shape: x, y, labels -> sim, probs, loss, dx, dy
   head_golden.npz        VecSimClassificationHead (with dense+tanh) and TwoTowerClassificationHead
   retrieval_golden.npz   all-pairs scores by the reference's pairwise modules + stable top-k
+  kg_golden.npz          TransE candidate ranking by the reference's vendored torchkge (tails and heads, L1 and L2)
   submit_golden.npz      submit/deepAI_result.jsonl scores/thresholds/labels (known answer: 5319
                          positives of 15909) and the commented softmax-head weights of
                          submit/similarity.py:5-18 with outputs of its numpy body (:19-24)
@@ -227,7 +228,46 @@ def gen_submit():
     np.savez_compressed(os.path.join(HERE, "submit_golden.npz"), **out)
 
 
+def gen_kg():
+    """TransE link-prediction ranking from the reference's vendored torchkge (torchkge/torchkge/inference.py:216-246 calls
+    model.inference_prepare_candidates + inference_scoring_function, then scores.sort(descending=True))."""
+    sys.path.insert(0, os.path.join(REF, "torchkge"))
+    from torchkge.models import TransEModel
+    out = {}
+    gen = torch.Generator().manual_seed(5)
+    n_ent, n_rel, dim, n = 700, 9, 64, 48
+    for kind in ("L1", "L2"):
+        model = TransEModel(dim, n_ent, n_rel, dissimilarity_type=kind)
+        with torch.no_grad():
+            model.ent_emb.weight.copy_(torch.randn(n_ent, dim, generator=gen) * 0.5)
+            model.rel_emb.weight.copy_(torch.randn(n_rel, dim, generator=gen) * 0.5)
+            model.ent_emb.weight[5] = model.ent_emb.weight[3]          # duplicate entities: exact score ties
+            model.ent_emb.weight[400] = model.ent_emb.weight[3]
+        ents = torch.randint(0, n_ent, (n,), generator=gen)
+        rels = torch.randint(0, n_rel, (n,), generator=gen)
+        out[f"{kind}/ent_emb"], out[f"{kind}/rel_emb"] = model.ent_emb.weight.detach().numpy(), model.rel_emb.weight.detach().numpy()
+        out[f"{kind}/ents"], out[f"{kind}/rels"] = ents.numpy(), rels.numpy()
+        with torch.no_grad():
+            for missing in ("tails", "heads"):
+                if missing == "heads":
+                    # EntityInference passes tensor([]) as h_idx here (inference.py:229), which makes the reference's
+                    # b_size 0 and the call crash (translation.py:226); any index vector of the batch length gives the
+                    # intended candidates view, h itself is unused
+                    _, t_emb, rel_emb, cands = model.inference_prepare_candidates(ents, ents, rels, entities=True)
+                    scores = model.inference_scoring_function(cands, t_emb, rel_emb)
+                else:
+                    h_emb, _, rel_emb, cands = model.inference_prepare_candidates(ents, torch.tensor([]).long(), rels, entities=True)
+                    scores = model.inference_scoring_function(h_emb, cands, rel_emb)
+                s, idx = scores.sort(descending=True, stable=True)
+                out[f"{kind}/{missing}/scores"] = scores.numpy()
+                out[f"{kind}/{missing}/top_idx"] = idx[:, :10].numpy()
+                out[f"{kind}/{missing}/top_scores"] = s[:, :10].numpy()
+    np.savez_compressed(os.path.join(HERE, "kg_golden.npz"), **out)
+    print("kg_golden:", len(out), "arrays")
+
+
 if __name__ == "__main__":
+    gen_kg()
     gen_pairs()
     gen_heads()
     gen_retrieval()

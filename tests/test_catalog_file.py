@@ -1,0 +1,129 @@
+"""CPU tests of the rank-4 "next" row: the binary catalog file, the native converter from the reference's
+embedding JSONL (finetune_text.py:784-792 / model_ensemble.py:112) and the oracle restatement of torchkge's candidate
+ranking against vectors produced by the reference's vendored torchkge (tests/golden/kg_golden.npz).  Host-side functions
+only: nothing here needs a GPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_import, torch_port
+
+
+def test_oracle_kg_ranking_matches_reference_torchkge(golden):
+    g = golden("kg_golden")
+    for kind in ("L1", "L2"):
+        ent, rel = torch.from_numpy(g[f"{kind}/ent_emb"]), torch.from_numpy(g[f"{kind}/rel_emb"])
+        ents, rels = torch.from_numpy(g[f"{kind}/ents"]), torch.from_numpy(g[f"{kind}/rels"])
+        for missing in ("tails", "heads"):
+            idx, top, scores = torch_port.kg_rank_entities(ent, rel, ents, rels, 10, missing, kind)
+            assert np.array_equal(scores.numpy(), g[f"{kind}/{missing}/scores"])
+            assert np.array_equal(idx.numpy(), g[f"{kind}/{missing}/top_idx"])
+            assert np.array_equal(top.numpy(), g[f"{kind}/{missing}/top_scores"])
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
+def test_catalog_file_round_trip(tmp_path, dt):
+    import item_alignment_b200 as ia
+    gen = torch.Generator().manual_seed(1)
+    m = torch.randn(37, 24, generator=gen).to(dt)
+    ids = [f"item-{i}" for i in range(36)] + ["ü-ñ-商品"]
+    path = tmp_path / "c.iacat"
+    ia.write_catalog(path, m, ids)
+    with ia.CatalogFile(path) as f:
+        assert (f.rows, f.dim, f.dtype, f.has_ids) == (37, 24, dt, True)
+        assert [f.id(i) for i in range(37)] == ids
+        a = f.numpy()
+        want = m.numpy() if dt == torch.float32 else m.view(torch.int16).numpy().view(np.uint16)
+        assert np.array_equal(a, want)
+        with pytest.raises(IndexError):
+            f.id(37)
+    ia.write_catalog(path, m)                      # no id table
+    with ia.CatalogFile(path) as f:
+        assert not f.has_ids and f.rows == 37
+        with pytest.raises(IndexError):
+            f.id(0)
+    assert os.path.getsize(path) == 4096 + 37 * 24 * m.element_size()
+
+
+def test_catalog_file_rejects_garbage(tmp_path):
+    import item_alignment_b200 as ia
+    bad = tmp_path / "bad.iacat"
+    bad.write_bytes(b"not a catalog" * 10)
+    with pytest.raises(ValueError):
+        ia.CatalogFile(bad)
+    with pytest.raises(ValueError):
+        ia.CatalogFile(tmp_path / "missing.iacat")
+    good = tmp_path / "good.iacat"
+    ia.write_catalog(good, torch.zeros(4, 8))
+    raw = bytearray(good.read_bytes())
+    raw[16:24] = (10 ** 9).to_bytes(8, "little")    # rows beyond the end of the file
+    good.write_bytes(bytes(raw))
+    with pytest.raises(ValueError):
+        ia.CatalogFile(good)
+
+
+def _write_reference_jsonl(path, n_pairs, dim, seed):
+    rng = np.random.default_rng(seed)
+    items = {f"{i:032x}": np.tanh(rng.standard_normal(dim)).astype(np.float32) * np.float32(10.0 ** rng.integers(-6, 3))
+             for i in range(n_pairs)}
+    keys = list(items)
+    with open(path, "w") as w:
+        for i in range(n_pairs):
+            s, t = keys[rng.integers(0, len(keys))], keys[rng.integers(0, len(keys))]
+            w.write(torch_port.embedding_jsonl_record(s, t, items[s], items[t], 0.5))
+        w.write("\n")                                # a trailing blank line
+    return items
+
+
+@pytest.mark.parametrize("side", ["src", "tgt", "both"])
+def test_jsonl_converter_matches_reference_reader(tmp_path, side):
+    import item_alignment_b200 as ia
+    src = tmp_path / "embeds.jsonl"
+    items = _write_reference_jsonl(src, 60, 48, seed=3)
+    ids, mat = torch_port.read_embedding_jsonl(src, side)
+    for dt in (torch.float32, torch.bfloat16, torch.float16):
+        out = tmp_path / f"embeds_{side}.iacat"
+        rows, dim = ia.jsonl_to_catalog(src, out, dt, side)
+        assert (rows, dim) == mat.shape
+        with ia.CatalogFile(out) as f:
+            assert [f.id(i) for i in range(rows)] == ids
+            got = f.numpy()
+            if dt == torch.float32:
+                assert np.array_equal(got, mat)                       # strtof returns the float32 the reference printed
+                assert all(np.array_equal(got[i], items[ids[i]]) for i in range(rows))
+            else:
+                want = torch.from_numpy(mat).to(dt).view(torch.int16).numpy().view(np.uint16)
+                assert np.array_equal(got, want)                      # round to nearest even, like torch's .to(dtype)
+
+
+def test_jsonl_converter_errors(tmp_path):
+    import item_alignment_b200 as ia
+    p = tmp_path / "ragged.jsonl"
+    with open(p, "w") as w:
+        w.write(torch_port.embedding_jsonl_record("a", "b", np.ones(4, np.float32), np.ones(4, np.float32), 0.5))
+        w.write(torch_port.embedding_jsonl_record("c", "d", np.ones(5, np.float32), np.ones(4, np.float32), 0.5))
+    with pytest.raises(ValueError):
+        ia.jsonl_to_catalog(p, tmp_path / "o.iacat")
+    p2 = tmp_path / "nokey.jsonl"
+    p2.write_text('{"src_item_id": "a", "threshold": 0.5}\n')
+    with pytest.raises(ValueError):
+        ia.jsonl_to_catalog(p2, tmp_path / "o.iacat")
+    with pytest.raises(ValueError):
+        ia.jsonl_to_catalog(tmp_path / "missing.jsonl", tmp_path / "o.iacat")
+    with pytest.raises(ValueError):
+        ia.jsonl_to_catalog(p, tmp_path / "o.iacat", side="left")
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (build container only)")
+def test_jsonl_converter_on_the_references_own_file(tmp_path):
+    """submit/deepAI_result.jsonl is the reference's own sample of this wire format (15 909 pairs, 1-d embeddings)."""
+    import item_alignment_b200 as ia
+    src = os.path.join(ref_import.reference_dir(), "submit", "deepAI_result.jsonl")
+    ids, mat = torch_port.read_embedding_jsonl(src, "tgt")
+    rows, dim = ia.jsonl_to_catalog(src, tmp_path / "deepai.iacat", torch.float32, "tgt")
+    assert (rows, dim) == mat.shape
+    with ia.CatalogFile(tmp_path / "deepai.iacat") as f:
+        assert np.array_equal(f.numpy(), mat)
+        assert [f.id(i) for i in (0, 1, rows - 1)] == [ids[0], ids[1], ids[-1]]
