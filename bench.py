@@ -11,6 +11,7 @@ Headline line (one JSON object on stdout, rank 0):
            region, loss read back)
   roofline achieved HBM GB/s of the fused kernel = algorithmic bytes (4*D*e + 16 per pair) / CUDA-event time
   cpu_baseline  the oracle port of the reference's modules timed on this box's host cores
+  projection    SURVEY 8f rank 1 (head projection + score in one launch) with the library sequence beside it (N = 1 only)
   retrieval     BASELINE config 4 (cosine top-100, 1M x 1024 bf16 catalog, 10 000 queries), catalog rows sharded
                 over the N ranks, per-shard top-k merged after one NCCL all-gather: queries/s + tensor roofline
 With N > 1 the pair path is replicated (weak scaling, no data-path collective); retrieval is strong scaling.
@@ -195,6 +196,54 @@ def bench_retrieval(torch, dist, ia, device, rank, world, pk):
     }
 
 
+def bench_projection(torch, ia, device, pk):
+    """head projection (dense -> tanh, both sides) + cosine score from the encoder features in one
+    launch, 65 536 pairs, K = H = 1024, bf16; the library sequence the reference runs is timed beside it."""
+    import item_alignment_b200.functional as F_
+    n, k, h = N_PAIRS, DIM, DIM
+    gen = torch.Generator(device=device).manual_seed(SEED + 6000)
+    f1 = torch.randn(n, k, device=device, generator=gen).to(torch.bfloat16)
+    f2 = torch.randn(n, k, device=device, generator=gen).to(torch.bfloat16)
+    w = (torch.randn(h, k, device=device, generator=gen) / k ** 0.5).to(torch.bfloat16)
+    b = torch.randn(h, device=device, generator=gen) * 0.1
+    bt = b.to(torch.bfloat16)
+
+    def timed(fn, warm=3, steps=20):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    def library():
+        x = torch.tanh(torch.nn.functional.linear(f1, w, bt))
+        y = torch.tanh(torch.nn.functional.linear(f2, w, bt))
+        s = torch.nn.functional.cosine_similarity(x, y)
+        return s, (s + 1) / 2
+
+    l0 = ia.launch_count()
+    ms_score = timed(lambda: F_.project_score_raw("cosine", f1, f2, w, b))
+    launches = ia.launch_count() - l0
+    ms_proj = timed(lambda: F_.project_tanh_raw(f1, f2, w, b))
+    ms_lib = timed(library)
+    flops = 2.0 * 2 * n * k * h
+    tf = flops / (ms_score * 1e-3) / 1e12
+    return {
+        "metric": "pairs/s (head projection + cosine score from encoder features)", "value": n / (ms_score * 1e-3), "unit": "pairs/s",
+        "ms_per_step": ms_score, "steps": 20, "warmup": 3, "dtype": "bf16",
+        "config": {"workload": "VecSimClassificationHead inference: tanh(dense(f)) for both sides + cosine score + probability, "
+                               "65536 pairs, K = H = 1024 (SURVEY 8f rank 1); embeddings not written"},
+        "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"],
+                     "traffic": None, "peak_source": pk["source"] + " (cuBLAS bf16 sustained)", "frac_of_burst": tf / pk["tf_burst"]},
+        "projection_only_ms": ms_proj, "library_linear_tanh_cosine_ms": ms_lib, "gpu_launches": launches,
+    }
+
+
 def main():
     # stdout carries exactly ONE JSON line: everything libraries print (e.g. "NCCL version ...") goes to stderr
     real_stdout = os.dup(1)
@@ -302,6 +351,10 @@ def main():
         del x, y
         torch.cuda.empty_cache()
         retrieval = bench_retrieval(torch, dist, ia, device, rank, world, pk)
+    projection = None
+    if not args.no_retrieval and world == 1:
+        torch.cuda.empty_cache()
+        projection = bench_projection(torch, ia, device, pk)
     t_end = time.time()
     clocks = sampler.stop(t_start, t_end) if sampler else None
 
@@ -334,7 +387,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": traffic,
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": pk["source"] + " (copy bandwidth)",
                          "frac_of_nominal_8000": gbs / 8000.0, "per_gpu": True},
-            "cpu_baseline": cpu, "retrieval": retrieval,
+            "cpu_baseline": cpu, "retrieval": retrieval, "projection": projection,
         }
         emit(line)
     if world > 1:
