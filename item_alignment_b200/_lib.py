@@ -9,6 +9,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libia_b200.so")
+LIB_PATH = os.environ.get("IA_B200_LIB", LIB_PATH)      # A/B builds of the same ABI (scripts/), never a fallback
 
 # enums of include/ia_b200.h
 MEASURES = {"inner_product": 0, "cosine": 1, "l1": 2, "l2": 3}

@@ -63,6 +63,11 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
                : "l"(p));
   return r;
 }
+__device__ __forceinline__ uint4 ldg_cs(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ void stg_stream(uint4* p, const uint4& v) {
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
                "r"(v.z), "r"(v.w)

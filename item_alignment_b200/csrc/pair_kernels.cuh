@@ -7,6 +7,9 @@
 // dx, dy are produced from the same registers and written once with 128-bit stores.
 // Algorithmic traffic: forward 2*D*e + 8 B/pair, fused forward+backward 4*D*e + 16 B/pair.
 #pragma once
+#ifndef IA_LOAD_SHAPE
+#define IA_LOAD_SHAPE 1   // 1: loads pinned in address order (see the load loop); 0: compiler's order (A/B builds)
+#endif
 #include <cstdlib>
 
 #include "common.cuh"
@@ -40,6 +43,7 @@ struct PairParams {
   float grad_scale;            // upstream * (1/n for mean)
   double loss_scale;           // 1/n for mean, 1 otherwise
   void* workspace;
+  int load_mode;               // bit 1: ld.global.cs instead of the no-allocate loads (0 in production; see the load loop)
 };
 
 // Per-pair sums gathered in one sweep over the registers.
@@ -181,8 +185,17 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
         for (int i = 0; i < VPL; ++i) {
           const int v = lane + 32 * i;
           if (live[k] && v < nvec) {
+#if IA_LOAD_SHAPE == 1
+            // The loads of a row group must ISSUE in address order (x0 y0 x1 y1 ... row by row): left to itself ptxas
+            // shuffles the independent loads of one basic block (e.g. +0x200, +0x200', +0, +0x400, ...) and C2 drops from
+            // 89.5 % to 85.7 % of the copy peak (profiles/r01/pair_load_order_ab.log).  A runtime-selectable cache operator
+            // (load_mode bit 1, never set in production) puts every load pair in its own basic block, which pins the order.
+            if (p.load_mode & 2) { xv[k][i] = ldg_cs(xr + v); yv[k][i] = ldg_cs(yr + v); }
+            else { xv[k][i] = ldg_stream(xr + v); yv[k][i] = ldg_stream(yr + v); }
+#else
             xv[k][i] = ldg_stream(xr + v);
             yv[k][i] = ldg_stream(yr + v);
+#endif
           } else {
             xv[k][i] = make_uint4(0, 0, 0, 0);
             yv[k][i] = make_uint4(0, 0, 0, 0);
