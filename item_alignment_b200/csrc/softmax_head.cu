@@ -34,6 +34,7 @@ struct HeadParams {
   void* workspace;    // [kWorkspaceBytes | float partial[grid][2h+2]]
   int stages;         // ring depth (TRAIN)
   int group;          // adjacent pairs per ring stage (TRAIN): 2 for rows <= 3 KB, else 1
+  int load_mode;      // bit 1: ld.global.cs (never set in production; pins the load order of the forward kernel)
 };
 
 constexpr int kHeadMaxGrid = 592;  // 148 SMs x 4
@@ -181,7 +182,11 @@ __global__ void __launch_bounds__(256, TRAIN ? 1 : 2) softmax_head_kernel(const 
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
           const int v = lane + 32 * i;
-          if (live[k] && v < nvec) { xv[k][i] = ldg_stream(xr + v); yv[k][i] = ldg_stream(yr + v); }
+          if (live[k] && v < nvec) {
+            // loads pinned in address order: one basic block per pair (see pair_kernels.cuh, load loop)
+            if (p.load_mode & 2) { xv[k][i] = ldg_cs(xr + v); yv[k][i] = ldg_cs(yr + v); }
+            else { xv[k][i] = ldg_stream(xr + v); yv[k][i] = ldg_stream(yr + v); }
+          }
           else { xv[k][i] = make_uint4(0, 0, 0, 0); yv[k][i] = make_uint4(0, 0, 0, 0); }
         }
       }
