@@ -447,6 +447,7 @@ extern "C" {
 int ia_project_tanh_fwd(int dtype, const void* f1, const void* f2, int64_t ldf1, int64_t ldf2, int64_t n, int64_t k_in,
                         const void* w, int64_t ldw, const float* bias, int64_t h, void* x, void* y, int64_t ldx, int64_t ldy,
                         ia_stream_t stream) {
+  if (n == 0) return IA_OK;   // empty batch: nothing to do (the reference returns empty tensors)
   ProjPlan pl;
   int rc = make_plan(n, k_in, h, &pl);
   if (rc != IA_OK) return rc;
@@ -472,6 +473,7 @@ int ia_project_score_fwd(int measure, int dtype, const void* f1, const void* f2,
                          int64_t k_in, const void* w, int64_t ldw, const float* bias, int64_t h, void* x, void* y, int64_t ldx,
                          int64_t ldy, float* sim, float* probs, double threshold, uint8_t* labels_out, void* workspace,
                          size_t workspace_bytes, ia_stream_t stream) {
+  if (n == 0) return IA_OK;
   ProjPlan pl;
   int rc = make_plan(n, k_in, h, &pl);
   if (rc != IA_OK) return rc;

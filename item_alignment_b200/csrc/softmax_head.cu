@@ -57,7 +57,10 @@ constexpr int kHeadMaxStages = 4;   // rows in flight per warp in the bulk-copy 
 // exactly the vectors it will consume: no cross-lane synchronisation), p.stages row groups in flight per warp.
 // (Measured first: a cp.async.bulk ring and a 16-warp variant both sat at 55 % -- the W re-reads were the limit.)
 // The forward-only kernel is light: plain streaming loads, RR = 1.
-template <typename T, typename G, bool TRAIN, int VPL, int RR>
+// FULL: h fills every lane's VPL vectors exactly (nvec == 32 * VPL): the per-vector bounds tests disappear.  Rows past the end
+// of the batch (last group only) are CLAMPED to the last row for loading and masked at the stores (delta = 0), so the
+// hot loop has no data-dependent branches.
+template <typename T, typename G, bool TRAIN, int VPL, int RR, bool FULL>
 __global__ void __launch_bounds__(256, TRAIN ? 1 : 2) softmax_head_kernel(const HeadParams p) {
   constexpr int NW = 8;
   constexpr int E = VecTraits<T>::kElems;
@@ -107,15 +110,15 @@ __global__ void __launch_bounds__(256, TRAIN ? 1 : 2) softmax_head_kernel(const 
     if (grp < n_groups) {
 #pragma unroll
       for (int k = 0; k < RR; ++k) {
-        const int64_t row = grp * RR + k;
-        if (row < p.n) {
+        const int64_t row = min(grp * RR + k, p.n - 1);
+        {
           const uint32_t dst = smem_u32(ring + (size_t)stage * stage_bytes + (size_t)k * 2 * row_bytes);
           const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + row * p.ldx);
           const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + row * p.ldy);
 #pragma unroll
           for (int i = 0; i < VPL; ++i) {
             const int v = lane + 32 * i;
-            if (v < nvec) {
+            if (FULL || v < nvec) {
               asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)v * 16u), "l"(xr + v) : "memory");
               asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + row_bytes + (uint32_t)v * 16u), "l"(yr + v) : "memory");
             }
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(256, TRAIN ? 1 : 2) softmax_head_kernel(const 
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
           const int v = lane + 32 * i;
-          if (live[k] && v < nvec) { xv[k][i] = xs[v]; yv[k][i] = ys[v]; }
+          if (FULL || v < nvec) { xv[k][i] = xs[v]; yv[k][i] = ys[v]; }
           else { xv[k][i] = make_uint4(0, 0, 0, 0); yv[k][i] = make_uint4(0, 0, 0, 0); }
         }
       }
@@ -177,12 +180,13 @@ __global__ void __launch_bounds__(256, TRAIN ? 1 : 2) softmax_head_kernel(const 
     } else {
 #pragma unroll
       for (int k = 0; k < RR; ++k) {
-        const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + rows[k] * p.ldx);
-        const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + rows[k] * p.ldy);
+        const int64_t rl = min(rows[k], p.n - 1);
+        const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + rl * p.ldx);
+        const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + rl * p.ldy);
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
           const int v = lane + 32 * i;
-          if (live[k] && v < nvec) {
+          if (FULL || v < nvec) {
             // loads pinned in address order: one basic block per pair (see pair_kernels.cuh, load loop)
             if (p.load_mode & 2) { xv[k][i] = ldg_cs(xr + v); yv[k][i] = ldg_cs(yr + v); }
             else { xv[k][i] = ldg_stream(xr + v); yv[k][i] = ldg_stream(yr + v); }
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(256, TRAIN ? 1 : 2) softmax_head_kernel(const 
     for (int k = 0; k < RR; ++k) { l0[k] = 0.f; l1[k] = 0.f; l0b[k] = 0.f; l1b[k] = 0.f; }
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      if (lane + 32 * i < nvec) {
+      if (FULL || lane + 32 * i < nvec) {
 #pragma unroll
         for (int q = 0; q < C; ++q) {
           const int f4 = (i * C + q) * 32 + lane;
@@ -246,14 +250,13 @@ __global__ void __launch_bounds__(256, TRAIN ? 1 : 2) softmax_head_kernel(const 
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int v = lane + 32 * i;
-      if (v < nvec) {
+      if (FULL || v < nvec) {
         float4 d0[C], d1[C];
 #pragma unroll
         for (int q = 0; q < C; ++q) { d0[q] = wdx[(i * C + q) * 32 + lane]; d1[q] = wdy[(i * C + q) * 32 + lane]; }
 #pragma unroll
         for (int k = 0; k < RR; ++k) {
-          if (!live[k]) continue;
-          float fx[E], fy[E], gx[E], gy[E];
+          float fx[E], fy[E], gx[E], gy[E];   // a clamped (dead) row has delta = 0: it adds nothing and is not stored
           unpack<T>(xv[k][i], fx);
           unpack<T>(yv[k][i], fy);
 #pragma unroll
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(256, TRAIN ? 1 : 2) softmax_head_kernel(const 
             accx[i * E + j] = fmaf(delta[k], fx[j], accx[i * E + j]);
             accy[i * E + j] = fmaf(delta[k], fy[j], accy[i * E + j]);
           }
-          if (p.dx) {
+          if (p.dx && live[k]) {
             Packer<G, E>::store(static_cast<G*>(p.dx) + rows[k] * p.lddx + (int64_t)v * E, gx);
             Packer<G, E>::store(static_cast<G*>(p.dy) + rows[k] * p.lddy + (int64_t)v * E, gy);
           }
@@ -358,14 +361,15 @@ __global__ void __launch_bounds__(256) softmax_head_finalize(const float* partia
 
 template <typename T, typename G, bool TRAIN, int VPL, int RR>
 static int launch_head_rr(const HeadParams& p_in, int stages, size_t smem, cudaStream_t stream, float* dw, float* db) {
-  auto kernel = softmax_head_kernel<T, G, TRAIN, VPL, RR>;
+  const bool full = p_in.h / VecTraits<T>::kElems == 32 * VPL;
+  auto kernel = full ? softmax_head_kernel<T, G, TRAIN, VPL, RR, true> : softmax_head_kernel<T, G, TRAIN, VPL, RR, false>;
   HeadParams p = p_in;
   p.stages = stages;
   p.group = RR;
-  static size_t configured_smem = 0;
-  if (smem > configured_smem) {
+  static size_t configured_smem[2] = {0, 0};
+  if (smem > configured_smem[full]) {
     IA_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured_smem = smem;
+    configured_smem[full] = smem;
   }
   const int64_t groups = (p.n + RR - 1) / RR;
   int64_t want = (groups + 7) / 8;
@@ -414,10 +418,12 @@ static int launch_head(const HeadParams& p, bool train, cudaStream_t stream, flo
   const int nvec = p.h / VecTraits<T>::kElems;
   if (train) {
     if (nvec <= 64) return launch_head_one<T, G, true, 2>(p, stream, dw, db);
+    if (nvec <= 96) return launch_head_one<T, G, true, 3>(p, stream, dw, db);     // h = 768 in 16-bit types
     if (nvec <= 128) return launch_head_one<T, G, true, 4>(p, stream, dw, db);
     return launch_head_one<T, G, true, 8>(p, stream, dw, db);
   }
   if (nvec <= 64) return launch_head_one<T, G, false, 2>(p, stream, dw, db);
+  if (nvec <= 96) return launch_head_one<T, G, false, 3>(p, stream, dw, db);
   if (nvec <= 128) return launch_head_one<T, G, false, 4>(p, stream, dw, db);
   return launch_head_one<T, G, false, 8>(p, stream, dw, db);
 }

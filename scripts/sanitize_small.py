@@ -38,5 +38,20 @@ with ia.CatalogIndex(cat.float()) as idx:
 ia.merge_keys(torch.stack([keys, keys]), 10)
 emb = cat; F_.pair_score_gather_raw("cosine", emb, emb, torch.arange(100, device=dev), torch.arange(100, 200, device=dev))
 ia.threshold_sweep(torch.rand(5000, device=dev), (torch.rand(5000, device=dev) < 0.5).long())
+# head projection (tcgen05 GEMM + tanh epilogue, with and without the fused score; partial tiles in every dimension)
+for dt, n, k, h in ((torch.bfloat16, 300, 264, 136), (torch.float16, 129, 768, 768), (torch.bfloat16, 21, 48, 48)):
+    f1 = torch.randn(n, k, device=dev, generator=g).to(dt); f2 = torch.randn(n, k, device=dev, generator=g).to(dt)
+    w = (torch.randn(h, k, device=dev, generator=g) / k ** 0.5).to(dt); b = torch.randn(h, device=dev, generator=g) * 0.1
+    F_.project_tanh_raw(f1, f2, w, b)
+    for m in ("inner_product", "cosine", "l1", "l2"):
+        F_.project_score_raw(m, f1, f2, w, b, threshold=0.5, want_embeds=(m == "cosine"))
+# dissimilarity knobs + catalog file upload
+with ia.CatalogIndex(cat.float()) as idx:
+    idx.topk_dissimilarity(q.float(), 10, p=1); idx.topk_dissimilarity(q.float(), 10, p=2)
+import tempfile
+with tempfile.TemporaryDirectory() as td:
+    ia.write_catalog(td + "/c.iacat", cat.cpu(), [str(i) for i in range(cat.shape[0])])
+    with ia.CatalogFile(td + "/c.iacat") as f, f.index(100, 2900) as idx:
+        idx.topk(q, 5, "cosine")
 torch.cuda.synchronize()
 print("sanitize_small: done")

@@ -276,6 +276,44 @@ def test_softmax_head_golden_and_reference_weights(golden, F_):
         np.testing.assert_allclose(probs[:, 1].cpu().numpy(), s[f"softmax/{i}/p1"], rtol=2e-5)
 
 
+@pytest.mark.parametrize("n,h,dt", [
+    (5001, 1024, torch.bfloat16),     # two rows per W read, every lane full, odd n: the last group has a clamped row
+    (4100, 768, torch.bfloat16),      # three vectors per lane (h = 768)
+    (4097, 1000, torch.bfloat16),     # partial last vector
+    (4500, 512, torch.float32),       # fp32, two rows per W read
+    (4099, 1024, torch.float32),      # fp32, eight vectors per lane, one row per W read
+    (300, 1024, torch.float16),       # small batch: one row per iteration
+    (4096, 264, torch.float16),
+])
+def test_softmax_head_ce_vs_oracle_all_kernel_variants(n, h, dt, F_):
+    """Seeded shapes that reach every softmax-head kernel variant (ring depth, rows per W read, full / partial lanes),
+    forward-only and training, against the oracle restatement of TwoTowerClassificationHead + CrossEntropyLoss."""
+    from oracle import torch_port
+    gen = torch.Generator().manual_seed(n + h)
+    x = torch.tanh(torch.randn(n, h, generator=gen)).to(dt)
+    y = torch.tanh(torch.randn(n, h, generator=gen)).to(dt)
+    w = torch.randn(2, 2 * h, generator=gen) * 0.05
+    b = torch.randn(2, generator=gen) * 0.05
+    labels = (torch.rand(n, generator=gen) < 0.5).long()
+    rl, rp, rloss, rdx, rdy, rdw, rdb = torch_port.softmax_head_ce_fwd_bwd(x.float(), y.float(), w, b, labels)
+    logits, probs, loss, dx, dy, dw, db = F_.softmax_head_raw(x.to(DEV), y.to(DEV), w.to(DEV), b.to(DEV), labels.to(DEV))
+    term = float((x.float().abs() @ w[:, :h].abs().t() + y.float().abs() @ w[:, h:].abs().t()).max())
+    assert float((logits.cpu() - rl).abs().max()) <= 1e-5 * term
+    assert float((probs.cpu() - rp).abs().max()) <= 2e-5 * max(1.0, term)
+    np.testing.assert_allclose(float(loss), float(rloss), rtol=2e-5)
+    gtol = 2e-5 if dt == torch.float32 else (2.0 ** -8 if dt == torch.bfloat16 else 2.0 ** -10)
+    for ours, ref, name in ((dx, rdx, "dx"), (dy, rdy, "dy")):
+        err = (ours.float().cpu() - ref).abs()
+        floor = 2.0 ** -24 if dt == torch.float16 else 0.0        # fp16 gradients of a mean over n rows sit in the subnormals
+        assert float((err - gtol * ref.abs()).max()) <= 2e-5 * float(ref.abs().max()) + floor, name
+    for ours, ref, name in ((dw, rdw, "dw"), (db, rdb, "db")):
+        assert float((ours.cpu() - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-7, name
+    # forward-only kernel: same logits / probabilities
+    l2, p2, _, _, _, _, _ = F_.softmax_head_raw(x.to(DEV), y.to(DEV), w.to(DEV), b.to(DEV))
+    assert float((l2.cpu() - rl).abs().max()) <= 1e-5 * term
+    assert float((p2.cpu() - rp).abs().max()) <= 2e-5 * max(1.0, term)
+
+
 def test_vecsim_head_golden_and_fused_step(golden):
     import types
     import item_alignment_b200 as ia

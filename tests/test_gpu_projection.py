@@ -164,6 +164,16 @@ def test_head_module_uses_fused_projection():
     assert head.dense.weight.grad is not None and bool(torch.isfinite(head.dense.weight.grad).all())
 
 
+def test_project_empty_batch():
+    import item_alignment_b200.functional as F_
+    f = torch.zeros(0, 64, device=DEV, dtype=torch.bfloat16)
+    w = torch.randn(32, 64, device=DEV).bfloat16()
+    x, y = F_.project_tanh_raw(f, f, w, None)
+    assert x.shape == (0, 32) and y.shape == (0, 32)
+    sim, probs = F_.project_score("cosine", f, f, w, None)
+    assert sim.shape == (0,) and probs.shape == (0,)
+
+
 def test_project_rejects_what_it_cannot_do():
     import item_alignment_b200.functional as F_
     f = torch.randn(8, 64, device=DEV)
