@@ -9,6 +9,8 @@
 // reduced block -> workspace -> finalize kernel in a fixed order (bit-reproducible run to run).
 // Two classes: delta = p1 - label is formed without cancellation (label 1 -> -p0), dlogit1 = delta,
 // dlogit0 = -delta, so dW[0] = -dW[1] and db[0] = -db[1].
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -60,9 +62,12 @@ constexpr int kHeadMaxStages = 4;   // rows in flight per warp in the bulk-copy 
 // FULL: h fills every lane's VPL vectors exactly (nvec == 32 * VPL): the per-vector bounds tests disappear.  Rows past the end
 // of the batch (last group only) are CLAMPED to the last row for loading and masked at the stores (delta = 0), so the
 // hot loop has no data-dependent branches.
-template <typename T, typename G, bool TRAIN, int VPL, int RR, bool FULL>
-__global__ void __launch_bounds__(256, TRAIN ? 1 : 2) softmax_head_kernel(const HeadParams p) {
-  constexpr int NW = 8;
+// NW / REREAD: the 8-warp training kernel keeps the RR rows of an iteration in registers next to the dW accumulators (~250
+// registers per thread).  REREAD trades registers for shared-memory reads: rows stay in the ring and are read where they are
+// used (forward pass, then again in the gradient pass), which fits 12 warps per SM (3 per scheduler instead of 2) -- the
+// kernel is bound by dependent-issue latency, not by bandwidth.
+template <typename T, typename G, bool TRAIN, int VPL, int RR, bool FULL, int NW, bool REREAD>
+__global__ void __launch_bounds__(NW * 32, TRAIN ? 1 : 2) softmax_head_kernel(const HeadParams p) {
   constexpr int E = VecTraits<T>::kElems;
   constexpr int C = E / 4;            // float4 chunks per 128-bit input vector
   constexpr int P4 = VPL * 32 * C;    // float4 per (padded) weight-row half
@@ -77,26 +82,6 @@ __global__ void __launch_bounds__(256, TRAIN ? 1 : 2) softmax_head_kernel(const 
   float* sw = reinterpret_cast<float*>(smem4);
   float* sacc = sw + 24 * P4;
   const int h = p.h, h2 = 2 * p.h;
-  for (int i0 = threadIdx.x; i0 < h2; i0 += 4 * blockDim.x) {   // four independent loads in flight per thread
-    float a[4], c[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * blockDim.x;
-      a[u] = i < h2 ? __ldg(p.w + i) : 0.f;
-      c[u] = i < h2 ? __ldg(p.w + h2 + i) : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * blockDim.x;
-      if (i < h2) {
-        const int half = i >= h, e = half ? i - h : i;
-        const int pos = half * (4 * P4) + swz<E>(e);
-        sw[pos] = a[u];
-        sw[8 * P4 + pos] = c[u];
-        if (TRAIN) { sw[16 * P4 + pos] = c[u] - a[u]; sacc[i] = 0.f; }
-      }
-    }
-  }
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warps_total = (int64_t)gridDim.x * NW;
   const int nvec = h / E;
@@ -130,6 +115,27 @@ __global__ void __launch_bounds__(256, TRAIN ? 1 : 2) softmax_head_kernel(const 
   };
   if (TRAIN) {
     for (int s = 0; s < p.stages; ++s) arm(s, grp0 + s * warps_total);
+  }
+  // the W tiles are built while the first rows are already streaming in
+  for (int i0 = threadIdx.x; i0 < h2; i0 += 4 * blockDim.x) {   // four independent loads in flight per thread
+    float a[4], c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      a[u] = i < h2 ? __ldg(p.w + i) : 0.f;
+      c[u] = i < h2 ? __ldg(p.w + h2 + i) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < h2) {
+        const int half = i >= h, e = half ? i - h : i;
+        const int pos = half * (4 * P4) + swz<E>(e);
+        sw[pos] = a[u];
+        sw[8 * P4 + pos] = c[u];
+        if (TRAIN) { sw[16 * P4 + pos] = c[u] - a[u]; sacc[i] = 0.f; }
+      }
+    }
   }
   __syncthreads();
   const float b0 = p.b[0], b1 = p.b[1];
@@ -165,18 +171,20 @@ __global__ void __launch_bounds__(256, TRAIN ? 1 : 2) softmax_head_kernel(const 
       else if (p.stages == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
       else if (p.stages == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
       else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (!REREAD) {
 #pragma unroll
-      for (int k = 0; k < RR; ++k) {
-        const uint4* xs = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_bytes + (size_t)k * 2 * row_bytes);
-        const uint4* ys = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_bytes + (size_t)k * 2 * row_bytes + row_bytes);
+        for (int k = 0; k < RR; ++k) {
+          const uint4* xs = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_bytes + (size_t)k * 2 * row_bytes);
+          const uint4* ys = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_bytes + (size_t)k * 2 * row_bytes + row_bytes);
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-          const int v = lane + 32 * i;
-          if (FULL || v < nvec) { xv[k][i] = xs[v]; yv[k][i] = ys[v]; }
-          else { xv[k][i] = make_uint4(0, 0, 0, 0); yv[k][i] = make_uint4(0, 0, 0, 0); }
+          for (int i = 0; i < VPL; ++i) {
+            const int v = lane + 32 * i;
+            if (FULL || v < nvec) { xv[k][i] = xs[v]; yv[k][i] = ys[v]; }
+            else { xv[k][i] = make_uint4(0, 0, 0, 0); yv[k][i] = make_uint4(0, 0, 0, 0); }
+          }
         }
+        arm(stage, grp + (int64_t)p.stages * warps_total);   // the slot is in registers now: refill it
       }
-      arm(stage, grp + (int64_t)p.stages * warps_total);   // the slot is in registers now: refill it
     } else {
 #pragma unroll
       for (int k = 0; k < RR; ++k) {
@@ -199,26 +207,35 @@ __global__ void __launch_bounds__(256, TRAIN ? 1 : 2) softmax_head_kernel(const 
     float l0[RR], l1[RR], l0b[RR], l1b[RR];
 #pragma unroll
     for (int k = 0; k < RR; ++k) { l0[k] = 0.f; l1[k] = 0.f; l0b[k] = 0.f; l1b[k] = 0.f; }
+    // row vector (k, i) of this lane: from registers, or (REREAD) from the ring slot it was copied into
+    const uint4* ring_stage = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_bytes);
+    const int row_vecs = (int)(row_bytes / 16);
+    auto x_vec = [&](int k, int i) -> uint4 { return (TRAIN && REREAD) ? ring_stage[(2 * k) * row_vecs + lane + 32 * i] : xv[k][i]; };
+    auto y_vec = [&](int k, int i) -> uint4 { return (TRAIN && REREAD) ? ring_stage[(2 * k + 1) * row_vecs + lane + 32 * i] : yv[k][i]; };
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       if (FULL || lane + 32 * i < nvec) {
+        float4 a0[C], a1[C], c0[C], c1[C];
 #pragma unroll
         for (int q = 0; q < C; ++q) {
           const int f4 = (i * C + q) * 32 + lane;
-          const float4 a0 = w0x[f4], a1 = w0y[f4], c0 = w1x[f4], c1 = w1y[f4];
+          a0[q] = w0x[f4]; a1[q] = w0y[f4]; c0[q] = w1x[f4]; c1[q] = w1y[f4];
+        }
 #pragma unroll
-          for (int k = 0; k < RR; ++k) {
-            float fx[E], fy[E];
-            unpack<T>(xv[k][i], fx);
-            unpack<T>(yv[k][i], fy);
-            l0[k] = fmaf(fx[4 * q + 0], a0.x, l0[k]); l0[k] = fmaf(fx[4 * q + 1], a0.y, l0[k]);
-            l0[k] = fmaf(fx[4 * q + 2], a0.z, l0[k]); l0[k] = fmaf(fx[4 * q + 3], a0.w, l0[k]);
-            l0b[k] = fmaf(fy[4 * q + 0], a1.x, l0b[k]); l0b[k] = fmaf(fy[4 * q + 1], a1.y, l0b[k]);
-            l0b[k] = fmaf(fy[4 * q + 2], a1.z, l0b[k]); l0b[k] = fmaf(fy[4 * q + 3], a1.w, l0b[k]);
-            l1[k] = fmaf(fx[4 * q + 0], c0.x, l1[k]); l1[k] = fmaf(fx[4 * q + 1], c0.y, l1[k]);
-            l1[k] = fmaf(fx[4 * q + 2], c0.z, l1[k]); l1[k] = fmaf(fx[4 * q + 3], c0.w, l1[k]);
-            l1b[k] = fmaf(fy[4 * q + 0], c1.x, l1b[k]); l1b[k] = fmaf(fy[4 * q + 1], c1.y, l1b[k]);
-            l1b[k] = fmaf(fy[4 * q + 2], c1.z, l1b[k]); l1b[k] = fmaf(fy[4 * q + 3], c1.w, l1b[k]);
+        for (int k = 0; k < RR; ++k) {
+          float fx[E], fy[E];
+          unpack<T>(x_vec(k, i), fx);
+          unpack<T>(y_vec(k, i), fy);
+#pragma unroll
+          for (int q = 0; q < C; ++q) {
+            l0[k] = fmaf(fx[4 * q + 0], a0[q].x, l0[k]); l0[k] = fmaf(fx[4 * q + 1], a0[q].y, l0[k]);
+            l0[k] = fmaf(fx[4 * q + 2], a0[q].z, l0[k]); l0[k] = fmaf(fx[4 * q + 3], a0[q].w, l0[k]);
+            l0b[k] = fmaf(fy[4 * q + 0], a1[q].x, l0b[k]); l0b[k] = fmaf(fy[4 * q + 1], a1[q].y, l0b[k]);
+            l0b[k] = fmaf(fy[4 * q + 2], a1[q].z, l0b[k]); l0b[k] = fmaf(fy[4 * q + 3], a1[q].w, l0b[k]);
+            l1[k] = fmaf(fx[4 * q + 0], c0[q].x, l1[k]); l1[k] = fmaf(fx[4 * q + 1], c0[q].y, l1[k]);
+            l1[k] = fmaf(fx[4 * q + 2], c0[q].z, l1[k]); l1[k] = fmaf(fx[4 * q + 3], c0[q].w, l1[k]);
+            l1b[k] = fmaf(fy[4 * q + 0], c1[q].x, l1b[k]); l1b[k] = fmaf(fy[4 * q + 1], c1[q].y, l1b[k]);
+            l1b[k] = fmaf(fy[4 * q + 2], c1[q].z, l1b[k]); l1b[k] = fmaf(fy[4 * q + 3], c1[q].w, l1b[k]);
           }
         }
       }
@@ -257,8 +274,8 @@ __global__ void __launch_bounds__(256, TRAIN ? 1 : 2) softmax_head_kernel(const 
 #pragma unroll
         for (int k = 0; k < RR; ++k) {
           float fx[E], fy[E], gx[E], gy[E];   // a clamped (dead) row has delta = 0: it adds nothing and is not stored
-          unpack<T>(xv[k][i], fx);
-          unpack<T>(yv[k][i], fy);
+          unpack<T>(x_vec(k, i), fx);
+          unpack<T>(y_vec(k, i), fy);
 #pragma unroll
           for (int q = 0; q < C; ++q) {
             gx[4 * q + 0] = delta[k] * d0[q].x; gx[4 * q + 1] = delta[k] * d0[q].y; gx[4 * q + 2] = delta[k] * d0[q].z; gx[4 * q + 3] = delta[k] * d0[q].w;
@@ -276,6 +293,7 @@ __global__ void __launch_bounds__(256, TRAIN ? 1 : 2) softmax_head_kernel(const 
         }
       }
     }
+    if (REREAD) arm(stage, grp + (int64_t)p.stages * warps_total);   // both passes have read the slot: refill it
   }
 
   if (TRAIN) {
@@ -359,10 +377,11 @@ __global__ void __launch_bounds__(256) softmax_head_finalize(const float* partia
   }
 }
 
-template <typename T, typename G, bool TRAIN, int VPL, int RR>
+template <typename T, typename G, bool TRAIN, int VPL, int RR, int NW = 8, bool REREAD = false>
 static int launch_head_rr(const HeadParams& p_in, int stages, size_t smem, cudaStream_t stream, float* dw, float* db) {
   const bool full = p_in.h / VecTraits<T>::kElems == 32 * VPL;
-  auto kernel = full ? softmax_head_kernel<T, G, TRAIN, VPL, RR, true> : softmax_head_kernel<T, G, TRAIN, VPL, RR, false>;
+  auto kernel = full ? softmax_head_kernel<T, G, TRAIN, VPL, RR, true, NW, REREAD>
+                     : softmax_head_kernel<T, G, TRAIN, VPL, RR, false, NW, REREAD>;
   HeadParams p = p_in;
   p.stages = stages;
   p.group = RR;
@@ -372,11 +391,11 @@ static int launch_head_rr(const HeadParams& p_in, int stages, size_t smem, cudaS
     configured_smem[full] = smem;
   }
   const int64_t groups = (p.n + RR - 1) / RR;
-  int64_t want = (groups + 7) / 8;
-  int64_t cap = (int64_t)sm_count() * (TRAIN ? 1 : blocks_per_sm(kernel, 256, smem));
+  int64_t want = (groups + NW - 1) / NW;
+  int64_t cap = (int64_t)sm_count() * (TRAIN ? 1 : blocks_per_sm(kernel, NW * 32, smem));
   if (cap > kHeadMaxGrid) cap = kHeadMaxGrid;
   const int grid = (int)(want < cap ? want : cap);
-  kernel<<<grid, 256, smem, stream>>>(p);
+  kernel<<<grid, NW * 32, smem, stream>>>(p);
   IA_LAUNCH_CHECK();
   if (TRAIN && (dw || db)) {
     const float* partials = reinterpret_cast<const float*>(static_cast<const char*>(p.workspace) + kWorkspaceBytes);
@@ -397,11 +416,19 @@ static int launch_head_one(const HeadParams& p, cudaStream_t stream, float* dw, 
   }
   const size_t fixed = w_bytes + (size_t)(((2 * p.h + 3) & ~3)) * 4;
   const size_t row_bytes = (size_t)p.h * sizeof(T);
-  auto fit = [&](int rr) {   // deepest ring that fits next to the W tiles (8 warps)
+  auto fit = [&](int rr, int nw = 8) {   // deepest ring that fits next to the W tiles
     int st = kHeadMaxStages;
-    while (st > 1 && fixed + (size_t)8 * st * rr * 2 * row_bytes > 227 * 1024) --st;
-    return (fixed + (size_t)8 * st * rr * 2 * row_bytes <= 227 * 1024) ? st : 0;
+    while (st > 1 && fixed + (size_t)nw * st * rr * 2 * row_bytes > 227 * 1024) --st;
+    return (fixed + (size_t)nw * st * rr * 2 * row_bytes <= 227 * 1024) ? st : 0;
   };
+  // 12 warps, rows re-read from the ring (see the kernel comment): 16-bit rows up to 2 KB, two stages of two rows per warp
+  static const int mode12 = [] { const char* e = getenv("IA_HEAD_12W"); return e ? atoi(e) : 1; }();
+  if (mode12 && VPL <= 4 && sizeof(T) == 2 && p.n >= 4096) {
+    const int st12 = fit(2, 12);
+    // park space of the block reduction: 12 warps x 2h floats must fit into the ring
+    if (st12 >= 2 && (size_t)12 * 2 * p.h * 4 <= (size_t)12 * st12 * 2 * 2 * row_bytes)
+      return launch_head_rr<T, G, true, (VPL <= 4 ? VPL : 4), 2, 12, true>(p, st12, fixed + (size_t)12 * st12 * 2 * 2 * row_bytes, stream, dw, db);
+  }
   // two rows per W read when the rows are small enough to keep both in registers (VPL <= 4) and the ring has >= 2 stages
   if (VPL <= 4 && p.n >= 4096) {
     const int st2 = fit(2);
