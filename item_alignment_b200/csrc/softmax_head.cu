@@ -416,8 +416,13 @@ static int launch_head_one(const HeadParams& p, cudaStream_t stream, float* dw, 
   }
   const size_t fixed = w_bytes + (size_t)(((2 * p.h + 3) & ~3)) * 4;
   const size_t row_bytes = (size_t)p.h * sizeof(T);
-  auto fit = [&](int rr, int nw = 8) {   // deepest ring that fits next to the W tiles
-    int st = kHeadMaxStages;
+  static const int max_stages = [] { const char* e = getenv("IA_HEAD_STAGES"); const int v = e ? atoi(e) : kHeadMaxStages; return v < 1 ? 1 : (v > kHeadMaxStages ? kHeadMaxStages : v); }();
+  // Ring depth: measured, MORE row data in flight is not better -- beyond ~128 KB per SM the memory system queues up and
+  // the kernel slows down (12 warps: 1 stage 103.2 us, 2 stages 108.3 us; 8 warps: 2 stages 109.5 us, 4 stages 111.5 us at
+  // 65 536 x 1024 bf16), so the depth is capped by bytes in flight, then by what fits next to the W tiles.
+  auto fit = [&](int rr, int nw = 8) {
+    int st = (int)((size_t)(128 * 1024) / ((size_t)nw * rr * 2 * row_bytes));
+    st = st < 1 ? 1 : (st > max_stages ? max_stages : st);
     while (st > 1 && fixed + (size_t)nw * st * rr * 2 * row_bytes > 227 * 1024) --st;
     return (fixed + (size_t)nw * st * rr * 2 * row_bytes <= 227 * 1024) ? st : 0;
   };
@@ -426,7 +431,7 @@ static int launch_head_one(const HeadParams& p, cudaStream_t stream, float* dw, 
   if (mode12 && VPL <= 4 && sizeof(T) == 2 && p.n >= 4096) {
     const int st12 = fit(2, 12);
     // park space of the block reduction: 12 warps x 2h floats must fit into the ring
-    if (st12 >= 2 && (size_t)12 * 2 * p.h * 4 <= (size_t)12 * st12 * 2 * 2 * row_bytes)
+    if (st12 >= 1 && (size_t)12 * 2 * p.h * 4 <= (size_t)12 * st12 * 2 * 2 * row_bytes)
       return launch_head_rr<T, G, true, (VPL <= 4 ? VPL : 4), 2, 12, true>(p, st12, fixed + (size_t)12 * st12 * 2 * 2 * row_bytes, stream, dw, db);
   }
   // two rows per W read when the rows are small enough to keep both in registers (VPL <= 4) and the ring has >= 2 stages
