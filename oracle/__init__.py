@@ -17,7 +17,12 @@ the input/output vectors under ``tests/golden/``.  ``tests/test_oracle_golden.py
 checks both oracle layers against those vectors and against the three weak
 artefacts the reference carries (``submit/deepAI_result.jsonl`` labels,
 the commented softmax-head weights of ``submit/similarity.py:5-24`` and the
-pure-Python inner product of ``pred_bert.py:47-52``).
+pure-Python inner product of ``pred_bert.py:47-52``).  The "next" rows are pinned the
+same way: ``kg_golden.npz`` holds candidate rankings computed by the reference's vendored
+torchkge (``TransEModel.inference_scoring_function`` + sort), checked bit for bit in
+``tests/test_catalog_file.py``; the embedding-JSONL reader restatement is checked (in the
+build container) on the reference's own ``submit/deepAI_result.jsonl``; the head projection
+uses the ``VecSimClassificationHead`` vectors of ``head_golden.npz``.
 
 Layers
 ------
