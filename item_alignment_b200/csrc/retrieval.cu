@@ -398,41 +398,76 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 
 // =============================================================================== CUDA-core kernel
 namespace simt {
-constexpr int BM = 64, BN = 128, BK = 32, THREADS = 256;
-constexpr int QS = BK * (BM + 1), CS = BK * (BN + 1), SS = BM * (BN + 1);
-constexpr int STAGE_FLOATS = (QS + CS) > SS ? (QS + CS) : SS;
-constexpr int SMEM_BYTES = STAGE_FLOATS * 4 + BM * kBufPitch * 8;
+constexpr int BM = 128, BN = 128, BK = 16, THREADS = 256;
+constexpr int AP = BM + 4;                        // pitch (floats) of the k-major staging tiles; multiple of 4: LDS.128
+constexpr int STAGE_FLOATS = 2 * BK * AP;         // one stage: A tile [BK][AP] + B tile [BK][AP]
+constexpr int SS = BM * (BN + 1);                 // score tile of the scan, aliases the two staging stages
+constexpr int TILE_FLOATS = (2 * STAGE_FLOATS) > SS ? (2 * STAGE_FLOATS) : SS;
+constexpr int SMEM_BYTES = TILE_FLOATS * 4 + BM * kBufPitch * 8;
+static_assert(BM == BN, "one loader serves both tiles");
 }  // namespace simt
 
-template <typename T, int MEASURE>
-__global__ void __launch_bounds__(simt::THREADS)
+// 8 consecutive elements of a row starting at column k0 as floats; `fill` where the row or the column does not exist.
+// VEC: rows are 16-byte aligned and d % 8 == 0, so one (16-bit types) or two (fp32) 128-bit loads do it.
+template <typename T, bool VEC>
+__device__ __forceinline__ void load8(const T* __restrict__ base, int64_t ld, int64_t row, int64_t rows, int k0, int d, float fill,
+                                      float (&out)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) out[j] = fill;
+  if (row >= rows) return;
+  const T* src = base + row * ld + k0;
+  if (VEC) {
+    if (k0 < d) {   // d % 8 == 0 and k0 % 8 == 0: all eight columns exist
+      if (sizeof(T) == 4) {
+        const uint4 u0 = ldg_stream(reinterpret_cast<const uint4*>(src));
+        const uint4 u1 = ldg_stream(reinterpret_cast<const uint4*>(src) + 1);
+        out[0] = __uint_as_float(u0.x); out[1] = __uint_as_float(u0.y); out[2] = __uint_as_float(u0.z); out[3] = __uint_as_float(u0.w);
+        out[4] = __uint_as_float(u1.x); out[5] = __uint_as_float(u1.y); out[6] = __uint_as_float(u1.z); out[7] = __uint_as_float(u1.w);
+      } else {
+        unpack<T>(ldg_stream(reinterpret_cast<const uint4*>(src)), out);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (k0 + j < d) out[j] = to_float<T>(src[j]);
+  }
+}
+
+// CUDA-core all-pairs kernel (l1 / l2, and any measure in fp32): 128 x 128 scores per CTA tile, 8 x 8 per thread, K in
+// blocks of 16 through two shared-memory stages (the next block's global loads are in flight while the current one is
+// multiplied), k-major tiles so that a thread's eight query values and eight catalog values are two LDS.128 each.
+template <typename T, int MEASURE, bool VEC>
+__global__ void __launch_bounds__(simt::THREADS, 2)
 retrieve_simt_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ cat, int64_t ldc, const RetrParams p) {
   using namespace simt;
   constexpr bool DESC = (MEASURE == IA_INNER || MEASURE == IA_COSINE);
   constexpr bool DIST = !DESC;
   extern __shared__ uint8_t smem_raw[];
-  float* Qs = reinterpret_cast<float*>(smem_raw);   // [BK][BM+1]
-  float* Cs = Qs + QS;                              // [BK][BN+1]
-  float* Ss = reinterpret_cast<float*>(smem_raw);   // [BM][BN+1] (aliases the staging tiles)
-  uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw + STAGE_FLOATS * 4);
+  float* tiles = reinterpret_cast<float*>(smem_raw);   // 2 stages x (A[BK][AP] | B[BK][AP])
+  float* Ss = reinterpret_cast<float*>(smem_raw);      // [BM][BN+1] (aliases the staging stages)
+  uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw + TILE_FLOATS * 4);
   TopKStats stats{0u, 0u, 0u, 0u};
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ty = tid >> 4, tx = tid & 15;
   const int n_items = p.n_qt * p.n_splits;
   const float eps = p.dist_eps;
+  // loader role: thread -> (row of the tile, half of the K block)
+  const int l_row = tid & (BM - 1), l_k = (tid >> 7) * 8;
+  const int kblocks = (p.d + BK - 1) / BK;
 
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int qt = item % p.n_qt, split = item / p.n_qt;
     const int t0 = split * p.tiles_per_split;
     const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
     const int q0 = qt * BM;
-    // top-k state: threads 0..63 own one query each (warps 0 and 1)
+    // top-k state: threads 0..127 own one query each (warps 0-3, like the four lane quarters of the tensor-core kernel)
     TopKThread st{0ull, 0};
-    uint64_t* lists_warp = p.lists + ((size_t)item * BM + warp * 32) * kListCap;
-    uint64_t* buf_warp = buf + (size_t)(warp * 32) * kBufPitch;
-    uint32_t* tau_warp = p.tau_global + qt * BM + warp * 32;
+    uint64_t* lists_warp = p.lists + ((size_t)item * BM + (warp & 3) * 32) * kListCap;
+    uint64_t* buf_warp = buf + (size_t)((warp & 3) * 32) * kBufPitch;
+    uint32_t* tau_warp = p.tau_global + qt * BM + (warp & 3) * 32;
     float qinv = 1.f;
-    if (warp < 2) {
+    if (warp < 4) {
       for (int i = lane; i < 32 * kListCap; i += 32) lists_warp[i] = 0ull;
       if (MEASURE == IA_COSINE) qinv = (q0 + tid < p.q_rows) ? __ldg(p.qinv + q0 + tid) : 0.f;
       __syncwarp();
@@ -441,37 +476,40 @@ retrieve_simt_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__
 
     for (int t = t0; t < t1; ++t) {
       const int64_t j0 = (int64_t)t * BN;
-      float acc[4][8];
+      float acc[8][8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-      for (int k0 = 0; k0 < p.d; k0 += BK) {
-        __syncthreads();   // previous tile's scan / previous k-block's compute done
-        for (int idx = tid; idx < BM * BK; idx += THREADS) {
-          const int row = idx / BK, kk = idx % BK;
-          float v = 0.f;
-          if (q0 + row < p.q_rows && k0 + kk < p.d) v = to_float<T>(q[(int64_t)(q0 + row) * ldq + k0 + kk]);
-          Qs[kk * (BM + 1) + row] = v;
+      float ra[8], rb[8];
+      // padded k / rows of the catalog: c = eps so that (0 - eps) + eps == 0 adds nothing to an l1 / l2 distance
+      load8<T, VEC>(q, ldq, q0 + l_row, p.q_rows, l_k, p.d, 0.f, ra);
+      load8<T, VEC>(cat, ldc, j0 + l_row, p.c_rows, l_k, p.d, DIST ? eps : 0.f, rb);
+      __syncthreads();   // previous tile's scan has finished with Ss (aliases the stages)
+      for (int kb = 0; kb < kblocks; ++kb) {
+        float* As = tiles + (kb & 1) * STAGE_FLOATS;
+        float* Bs = As + BK * AP;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          As[(l_k + j) * AP + l_row] = ra[j];
+          Bs[(l_k + j) * AP + l_row] = rb[j];
         }
-        for (int idx = tid; idx < BN * BK; idx += THREADS) {
-          const int row = idx / BK, kk = idx % BK;
-          // padded k / rows: c = eps so that (0 - eps) + eps == 0 adds nothing to an l1/l2 distance
-          float v = DIST ? p.dist_eps : 0.f;
-          if (j0 + row < p.c_rows && k0 + kk < p.d) v = to_float<T>(cat[(j0 + row) * ldc + k0 + kk]);
-          Cs[kk * (BN + 1) + row] = v;
+        __syncthreads();   // stage kb & 1 is complete; the other stage is free (its readers passed the previous barrier)
+        if (kb + 1 < kblocks) {   // next K block: global loads in flight during the multiply below
+          load8<T, VEC>(q, ldq, q0 + l_row, p.q_rows, (kb + 1) * BK + l_k, p.d, 0.f, ra);
+          load8<T, VEC>(cat, ldc, j0 + l_row, p.c_rows, (kb + 1) * BK + l_k, p.d, DIST ? eps : 0.f, rb);
         }
-        __syncthreads();
-#pragma unroll 4
+#pragma unroll 4   // 4 x 200 instructions: the fully unrolled block (51 KB of code) would not stay in the instruction cache
         for (int kk = 0; kk < BK; ++kk) {
-          float a[4], b[8];
+          const float4 a0 = *reinterpret_cast<const float4*>(&As[kk * AP + 4 * ty]);
+          const float4 a1 = *reinterpret_cast<const float4*>(&As[kk * AP + 64 + 4 * ty]);
+          const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk * AP + 4 * tx]);
+          const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk * AP + 64 + 4 * tx]);
+          const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) a[i] = Qs[kk * (BM + 1) + ty + 16 * i];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) b[j] = Cs[kk * (BN + 1) + tx + 16 * j];
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               if (DESC) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
@@ -483,14 +521,16 @@ retrieve_simt_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__
             }
         }
       }
-      __syncthreads();   // all warps done with Qs/Cs before Ss (alias) is written
+      __syncthreads();   // all warps done with the stages before Ss (alias) is written
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i) {
+        const int r = (i < 4 ? 0 : 64) + 4 * ty + (i & 3);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) Ss[(ty + 16 * i) * (BN + 1) + tx + 16 * j] = acc[i][j];
+        for (int j = 0; j < 8; ++j) Ss[r * (BN + 1) + (j < 4 ? 0 : 64) + 4 * tx + (j & 3)] = acc[i][j];
+      }
       __syncthreads();
 
-      if (warp < 2) {
+      if (warp < 4) {
         const bool q_ok = q0 + tid < p.q_rows;
         {
           const uint64_t gk = (uint64_t)(*reinterpret_cast<volatile uint32_t*>(tau_warp + lane)) << 32;
@@ -519,7 +559,7 @@ retrieve_simt_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__
         }
       }
     }
-    if (warp < 2) {
+    if (warp < 4) {
       __syncwarp();
       warp_compact(st, 1, p.k, buf_warp, lists_warp, tau_warp, stats);
       __threadfence();
@@ -817,16 +857,22 @@ static int catalog_topk_impl(ia_catalog* cat, int measure, float dist_eps, int d
       IA_LAUNCH_CHECK();
       return IA_OK;
     };
-#define IA_SIMT_DISPATCH(T)                                                                         \
-    switch (measure) {                                                                              \
-      case IA_INNER: rc = launch(retrieve_simt_kernel<T, IA_INNER>, (const T*)nullptr); break;      \
-      case IA_COSINE: rc = launch(retrieve_simt_kernel<T, IA_COSINE>, (const T*)nullptr); break;    \
-      case IA_L1: rc = launch(retrieve_simt_kernel<T, IA_L1>, (const T*)nullptr); break;            \
-      default: rc = launch(retrieve_simt_kernel<T, IA_L2>, (const T*)nullptr); break;               \
+    // 128-bit row loads when every 8-column group of every row is 16-byte aligned (32-byte for fp32 pairs is not needed)
+    const size_t esz = cat->dtype == IA_F32 ? 4 : 2;
+    const bool vec = cat->d % 8 == 0 && (ldq * esz) % 16 == 0 && (cat->ld * esz) % 16 == 0 &&
+                     reinterpret_cast<uintptr_t>(queries) % 16 == 0 && reinterpret_cast<uintptr_t>(cat->data) % 16 == 0;
+#define IA_SIMT_DISPATCH_V(T, V)                                                                       \
+    switch (measure) {                                                                                 \
+      case IA_INNER: rc = launch(retrieve_simt_kernel<T, IA_INNER, V>, (const T*)nullptr); break;      \
+      case IA_COSINE: rc = launch(retrieve_simt_kernel<T, IA_COSINE, V>, (const T*)nullptr); break;    \
+      case IA_L1: rc = launch(retrieve_simt_kernel<T, IA_L1, V>, (const T*)nullptr); break;            \
+      default: rc = launch(retrieve_simt_kernel<T, IA_L2, V>, (const T*)nullptr); break;               \
     }
+#define IA_SIMT_DISPATCH(T) if (vec) { IA_SIMT_DISPATCH_V(T, true) } else { IA_SIMT_DISPATCH_V(T, false) }
     if (cat->dtype == IA_F32) { IA_SIMT_DISPATCH(float) }
     else if (cat->dtype == IA_BF16) { IA_SIMT_DISPATCH(__nv_bfloat16) }
     else { IA_SIMT_DISPATCH(__half) }
+#undef IA_SIMT_DISPATCH_V
 #undef IA_SIMT_DISPATCH
     if (rc != IA_OK) return rc;
   }
