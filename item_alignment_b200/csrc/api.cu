@@ -30,6 +30,12 @@ int sm_count() {
   return cached[dev];
 }
 
+int device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev % kMaxDevices;
+}
+
 static size_t dtype_size(int dtype) { return dtype == IA_F32 ? 4 : 2; }
 
 static bool aligned16(const void* p, int64_t ld_elems, size_t esize) {

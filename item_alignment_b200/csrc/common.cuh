@@ -17,6 +17,8 @@ namespace ia {
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;
 int sm_count();  // SMs of the current device (cached per device)
+constexpr int kMaxDevices = 64;
+int device_slot();  // index of the current device in [0, kMaxDevices): per-device caches of function attributes
 
 #define IA_CUDA_CHECK(expr)                                                              \
   do {                                                                                   \

@@ -421,8 +421,9 @@ template <void (*kernel)(const PairParams)>
 int launch_rows_bulk(const PairParams& p, size_t elem_size, cudaStream_t stream) {
   constexpr int kThreads = 256, kWarps = 8;
   const size_t smem = (size_t)kWarps * kBulkStages * 2 * (size_t)p.d * elem_size + kWarps * kBulkStages * 8;
-  static size_t configured = 0;
+  static size_t configured_dev[kMaxDevices] = {};   // function attributes are per context: one slot per device
   static int cached_bps = 0;
+  size_t& configured = configured_dev[device_slot()];
   if (smem > configured) {
     IA_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

@@ -365,10 +365,11 @@ template <typename T, int MEASURE>
 static int launch_project(const CUtensorMap& m1, const CUtensorMap& m2, const CUtensorMap& mw, const ProjParams& p, int ctas,
                           cudaStream_t st) {
   auto kern = project_kernel<T, MEASURE>;
-  static bool configured = false;   // per instantiation
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};   // per instantiation and device (function attributes are per context)
+  const int slot = device_slot();
+  if (!configured[slot]) {
     IA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, proj::SMEM_BYTES));
-    configured = true;
+    configured[slot] = true;
   }
   const int items = p.n_rb * p.parts;
   kern<<<items < ctas ? items : ctas, proj::THREADS, proj::SMEM_BYTES, st>>>(m1, m2, mw, p);

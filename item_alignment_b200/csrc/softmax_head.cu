@@ -385,10 +385,11 @@ static int launch_head_rr(const HeadParams& p_in, int stages, size_t smem, cudaS
   HeadParams p = p_in;
   p.stages = stages;
   p.group = RR;
-  static size_t configured_smem[2] = {0, 0};
-  if (smem > configured_smem[full]) {
+  static size_t configured_smem[kMaxDevices][2] = {};   // function attributes are per context: one slot per device
+  const int slot = device_slot();
+  if (smem > configured_smem[slot][full]) {
     IA_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured_smem[full] = smem;
+    configured_smem[slot][full] = smem;
   }
   const int64_t groups = (p.n + RR - 1) / RR;
   int64_t want = (groups + NW - 1) / NW;
