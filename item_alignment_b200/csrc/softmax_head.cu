@@ -422,7 +422,8 @@ static int launch_head_one(const HeadParams& p, cudaStream_t stream, float* dw, 
   // the kernel slows down (12 warps: 1 stage 103.2 us, 2 stages 108.3 us; 8 warps: 2 stages 109.5 us, 4 stages 111.5 us at
   // 65 536 x 1024 bf16), so the depth is capped by bytes in flight, then by what fits next to the W tiles.
   auto fit = [&](int rr, int nw = 8) {
-    int st = (int)((size_t)(128 * 1024) / ((size_t)nw * rr * 2 * row_bytes));
+    static const size_t inflight = [] { const char* e = getenv("IA_HEAD_INFLIGHT_KB"); return (size_t)(e ? atoi(e) : 128) * 1024; }();
+    int st = (int)(inflight / ((size_t)nw * rr * 2 * row_bytes));
     st = st < 1 ? 1 : (st > max_stages ? max_stages : st);
     while (st > 1 && fixed + (size_t)nw * st * rr * 2 * row_bytes > 227 * 1024) --st;
     return (fixed + (size_t)nw * st * rr * 2 * row_bytes <= 227 * 1024) ? st : 0;
@@ -434,6 +435,12 @@ static int launch_head_one(const HeadParams& p, cudaStream_t stream, float* dw, 
     // park space of the block reduction: 12 warps x 2h floats must fit into the ring
     if (st12 >= 1 && (size_t)12 * 2 * p.h * 4 <= (size_t)12 * st12 * 2 * 2 * row_bytes)
       return launch_head_rr<T, G, true, (VPL <= 4 ? VPL : 4), 2, 12, true>(p, st12, fixed + (size_t)12 * st12 * 2 * 2 * row_bytes, stream, dw, db);
+  }
+  // fp32 rows are twice the bytes per element: one row per W read gives the same W traffic per byte as two 16-bit rows
+  if (mode12 && sizeof(T) == 4 && p.n >= 4096) {
+    const int st12 = fit(1, 12);
+    if (st12 >= 1 && (size_t)12 * 2 * p.h * 4 <= (size_t)12 * st12 * 2 * row_bytes)
+      return launch_head_rr<T, G, true, VPL, 1, 12, true>(p, st12, fixed + (size_t)12 * st12 * 2 * row_bytes, stream, dw, db);
   }
   // two rows per W read when the rows are small enough to keep both in registers (VPL <= 4) and the ring has >= 2 stages
   if (VPL <= 4 && p.n >= 4096) {

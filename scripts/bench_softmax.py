@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Softmax head (+ CE) timings, CUDA events: training and forward-only kernels for a few (dtype, h)."""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from item_alignment_b200 import functional as F_  # noqa: E402
+
+dev = "cuda:0"
+n = 65536
+
+
+def timed(fn, iters=30, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3
+
+
+for dt, h in ((torch.bfloat16, 1024), (torch.bfloat16, 768), (torch.float32, 1024), (torch.float32, 768), (torch.float16, 512)):
+    x = torch.tanh(torch.randn(n, h, device=dev)).to(dt)
+    y = torch.tanh(torch.randn(n, h, device=dev)).to(dt)
+    l = (torch.rand(n, device=dev) < 0.5).long()
+    w = torch.randn(2, 2 * h, device=dev) * 0.02
+    b = torch.zeros(2, device=dev)
+    e = x.element_size()
+    t_train = timed(lambda: F_.softmax_head_raw(x, y, w, b, l))
+    t_fwd = timed(lambda: F_.softmax_head_raw(x, y, w, b))
+    by_train, by_fwd = n * (4 * h * e + 24), n * (2 * h * e + 16)
+    print(f"{str(dt):16s} h={h:5d}: train {t_train:7.1f} us ({by_train / t_train / 1e3:6.0f} GB/s, {by_train / t_train / 1e3 / 65.549:5.1f} %)   "
+          f"forward {t_fwd:6.1f} us ({by_fwd / t_fwd / 1e3:6.0f} GB/s, {by_fwd / t_fwd / 1e3 / 65.549:5.1f} %)", flush=True)
