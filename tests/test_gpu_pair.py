@@ -284,6 +284,8 @@ def test_softmax_head_golden_and_reference_weights(golden, F_):
     (4099, 1024, torch.float32),      # fp32, eight vectors per lane, one row per W read
     (300, 1024, torch.float16),       # small batch: one row per iteration
     (4096, 264, torch.float16),
+    (8195, 768, torch.bfloat16),      # four rows per W read (small 16-bit rows, n >= 8192), tail group with three clamped rows
+    (9001, 264, torch.float16),
 ])
 def test_softmax_head_ce_vs_oracle_all_kernel_variants(n, h, dt, F_):
     """Seeded shapes that reach every softmax-head kernel variant (ring depth, rows per W read, full / partial lanes),
