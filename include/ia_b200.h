@@ -138,11 +138,13 @@ int ia_scale_inplace(int dtype, void* a, void* b, int64_t count, const float* g,
  * VecSimClassificationHead.forward (src/models/base.py:67-75; dense = nn.Linear(H*len(cls_layers) or H, H),
  * base.py:47-49) -- one tcgen05 GEMM for both sides with bias + tanh + rounding in its epilogue.
  * f1, f2: [n, k_in]; w: [h, k_in] (nn.Linear layout); bias: [h] fp32 or NULL; x, y: [n, h] in `dtype`.
+ * fast_tanh = 0: tanh to ~1e-6 relative in fp32, rounded once (the default everywhere in the Python mirror);
+ * fast_tanh = 1: the hardware tanh.approx (2^-11 relative: still within one bf16 ulp of the exact value) -- opt-in.
  * dtype is IA_BF16 or IA_F16 (fp32 -> IA_ERR_UNSUPPORTED: keep torch's GEMM); k_in, h and all leading
  * dimensions are multiples of 8 elements, pointers 16-byte aligned. */
 int ia_project_tanh_fwd(int dtype, const void* f1, const void* f2, int64_t ldf1, int64_t ldf2, int64_t n,
                         int64_t k_in, const void* w, int64_t ldw, const float* bias, int64_t h, void* x,
-                        void* y, int64_t ldx, int64_t ldy, ia_stream_t stream);
+                        void* y, int64_t ldx, int64_t ldy, int fast_tanh, ia_stream_t stream);
 /* The same GEMM with the pair score of base.py:77-86 computed in its epilogue from the rounded
  * embeddings (results equal ia_project_tanh_fwd followed by ia_pair_score_fwd up to fp32 summation
  * order); x and y may be NULL, in which case the embeddings never reach HBM (inference scoring).
@@ -155,8 +157,8 @@ int ia_project_last_stats(uint64_t* out8);
 int ia_project_score_fwd(int measure, int dtype, const void* f1, const void* f2, int64_t ldf1, int64_t ldf2,
                          int64_t n, int64_t k_in, const void* w, int64_t ldw, const float* bias, int64_t h,
                          void* x, void* y, int64_t ldx, int64_t ldy, float* sim, float* probs,
-                         double threshold, uint8_t* labels_out, void* workspace, size_t workspace_bytes,
-                         ia_stream_t stream);
+                         double threshold, uint8_t* labels_out, int fast_tanh, void* workspace,
+                         size_t workspace_bytes, ia_stream_t stream);
 
 /* ---- row inverse norms: 1 / max(||row||, eps) (cosine retrieval pre-pass, base.py:58 eps) ------ */
 int ia_row_inv_norm(int dtype, const void* x, int64_t n, int64_t d, int64_t ldx, float eps,

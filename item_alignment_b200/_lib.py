@@ -47,12 +47,12 @@ SIGNATURES = {
                                         c_int64, c_void_p, c_void_p, c_float, c_void_p, c_size_t, c_void_p]),
     "ia_scale_inplace": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "ia_project_tanh_fwd": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p,
-                                    c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+                                    c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "ia_project_last_stats": (c_int, [c_void_p]),
     "ia_project_score_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "ia_project_score_fwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64,
                                      c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_double,
-                                     c_void_p, c_void_p, c_size_t, c_void_p]),
+                                     c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "ia_row_inv_norm": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p]),
     "ia_catalog_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "ia_catalog_destroy": (None, [c_void_p]),

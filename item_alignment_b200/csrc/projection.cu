@@ -78,6 +78,17 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
   return v[0];
 }
 
+// FAST: the hardware approximation (one MUFU, relative error 2^-11 -- a quarter of a bf16 ulp, one fp16 ulp): an opt-in
+// speed / accuracy knob of the entry points, never the default.
+template <bool FAST> __device__ __forceinline__ float tanh_sel(float v) {
+  if (FAST) {
+    float r;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+  }
+  return tanh_f32(v);
+}
+
 template <typename T> __device__ __forceinline__ float round_to(float v, unsigned short& bits);
 template <> __device__ __forceinline__ float round_to<__nv_bfloat16>(float v, unsigned short& bits) {
   const __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -93,7 +104,7 @@ template <> __device__ __forceinline__ float round_to<__half>(float v, unsigned 
 // The accumulator is held TRANSPOSED: TMEM lane = output column (a row of W, the M operand), TMEM column = pair row
 // (columns 0-127: f1 rows -> x, 128-255: f2 rows -> y; [f1 tile; f2 tile] is one 256-row N operand).  One N=256 MMA per
 // K step moves 12 KB of operands per 128 tensor-core cycles (two N=128 MMAs would move 16 KB: shared-memory bound).
-template <typename T, int MEASURE>
+template <typename T, int MEASURE, bool FAST>
 __global__ void __launch_bounds__(proj::THREADS, 1)
 project_kernel(const __grid_constant__ CUtensorMap tmap_f1, const __grid_constant__ CUtensorMap tmap_f2,
                const __grid_constant__ CUtensorMap tmap_w, const ProjParams p) {
@@ -232,8 +243,8 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_f1, const __grid_constan
           float fx[32], fy[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            fx[i] = round_to<T>(tanh_f32(__uint_as_float(rx[i]) + bias), bx[i]);
-            fy[i] = round_to<T>(tanh_f32(__uint_as_float(ry[i]) + bias), by[i]);
+            fx[i] = round_to<T>(tanh_sel<FAST>(__uint_as_float(rx[i]) + bias), bx[i]);
+            fy[i] = round_to<T>(tanh_sel<FAST>(__uint_as_float(ry[i]) + bias), by[i]);
           }
           // a warp writes 32 consecutive columns of one row per store: 64 contiguous bytes
           const int rows_here = col_ok ? (int)min((int64_t)32, p.n - r_base) : 0;
@@ -361,10 +372,10 @@ static int make_plan(int64_t n, int64_t k_in, int64_t h, ProjPlan* pl) {
   return IA_OK;
 }
 
-template <typename T, int MEASURE>
+template <typename T, int MEASURE, bool FAST>
 static int launch_project(const CUtensorMap& m1, const CUtensorMap& m2, const CUtensorMap& mw, const ProjParams& p, int ctas,
                           cudaStream_t st) {
-  auto kern = project_kernel<T, MEASURE>;
+  auto kern = project_kernel<T, MEASURE, FAST>;
   static bool configured[kMaxDevices] = {};   // per instantiation and device (function attributes are per context)
   const int slot = device_slot();
   if (!configured[slot]) {
@@ -377,15 +388,15 @@ static int launch_project(const CUtensorMap& m1, const CUtensorMap& m2, const CU
   return IA_OK;
 }
 
-template <typename T>
+template <typename T, bool FAST>
 static int project_dispatch(int measure, const CUtensorMap& m1, const CUtensorMap& m2, const CUtensorMap& mw, const ProjParams& p,
                             int ctas, cudaStream_t st) {
   switch (measure) {
-    case proj::kNoScore: return launch_project<T, proj::kNoScore>(m1, m2, mw, p, ctas, st);
-    case IA_INNER: return launch_project<T, IA_INNER>(m1, m2, mw, p, ctas, st);
-    case IA_COSINE: return launch_project<T, IA_COSINE>(m1, m2, mw, p, ctas, st);
-    case IA_L1: return launch_project<T, IA_L1>(m1, m2, mw, p, ctas, st);
-    case IA_L2: return launch_project<T, IA_L2>(m1, m2, mw, p, ctas, st);
+    case proj::kNoScore: return launch_project<T, proj::kNoScore, FAST>(m1, m2, mw, p, ctas, st);
+    case IA_INNER: return launch_project<T, IA_INNER, FAST>(m1, m2, mw, p, ctas, st);
+    case IA_COSINE: return launch_project<T, IA_COSINE, FAST>(m1, m2, mw, p, ctas, st);
+    case IA_L1: return launch_project<T, IA_L1, FAST>(m1, m2, mw, p, ctas, st);
+    case IA_L2: return launch_project<T, IA_L2, FAST>(m1, m2, mw, p, ctas, st);
   }
   set_error("Unsupported similarty measure: %d", measure);
   return IA_ERR_INVALID;
@@ -401,7 +412,7 @@ static unsigned long long* proj_stats_buffer() {
   return g_proj_stats[dev];
 }
 
-static int project_common(int measure, int dtype, const void* f1, const void* f2, int64_t ldf1, int64_t ldf2, int64_t n,
+static int project_common(int measure, int fast_tanh, int dtype, const void* f1, const void* f2, int64_t ldf1, int64_t ldf2, int64_t n,
                           int64_t k_in, const void* w, int64_t ldw, const float* bias, int64_t h, void* x, void* y, int64_t ldx,
                           int64_t ldy, float4* sums, const ProjPlan& pl, cudaStream_t st) {
   if (dtype != IA_BF16 && dtype != IA_F16) {
@@ -435,8 +446,11 @@ static int project_common(int measure, int dtype, const void* f1, const void* f2
     if (p.stats != nullptr) IA_CUDA_CHECK(cudaMemsetAsync(p.stats, 0, 8 * sizeof(unsigned long long), st));
   }
   p.cts_per_part = pl.cts_per_part; p.bias = bias; p.x = x; p.y = y; p.ldx = ldx; p.ldy = ldy; p.sums = sums;
-  return dtype == IA_BF16 ? project_dispatch<__nv_bfloat16>(measure, m1, m2, mw, p, pl.ctas, st)
-                          : project_dispatch<__half>(measure, m1, m2, mw, p, pl.ctas, st);
+  if (fast_tanh)
+    return dtype == IA_BF16 ? project_dispatch<__nv_bfloat16, true>(measure, m1, m2, mw, p, pl.ctas, st)
+                            : project_dispatch<__half, true>(measure, m1, m2, mw, p, pl.ctas, st);
+  return dtype == IA_BF16 ? project_dispatch<__nv_bfloat16, false>(measure, m1, m2, mw, p, pl.ctas, st)
+                          : project_dispatch<__half, false>(measure, m1, m2, mw, p, pl.ctas, st);
 }
 
 }  // namespace ia
@@ -447,13 +461,13 @@ extern "C" {
 
 int ia_project_tanh_fwd(int dtype, const void* f1, const void* f2, int64_t ldf1, int64_t ldf2, int64_t n, int64_t k_in,
                         const void* w, int64_t ldw, const float* bias, int64_t h, void* x, void* y, int64_t ldx, int64_t ldy,
-                        ia_stream_t stream) {
+                        int fast_tanh, ia_stream_t stream) {
   if (n == 0) return IA_OK;   // empty batch: nothing to do (the reference returns empty tensors)
   ProjPlan pl;
   int rc = make_plan(n, k_in, h, &pl);
   if (rc != IA_OK) return rc;
   if (x == nullptr || y == nullptr) { set_error("projection: null output"); return IA_ERR_INVALID; }
-  return project_common(proj::kNoScore, dtype, f1, f2, ldf1, ldf2, n, k_in, w, ldw, bias, h, x, y, ldx, ldy, nullptr, pl,
+  return project_common(proj::kNoScore, fast_tanh, dtype, f1, f2, ldf1, ldf2, n, k_in, w, ldw, bias, h, x, y, ldx, ldy, nullptr, pl,
                         (cudaStream_t)stream);
 }
 
@@ -472,8 +486,8 @@ size_t ia_project_score_workspace_bytes(int64_t n, int64_t k_in, int64_t h) {
 
 int ia_project_score_fwd(int measure, int dtype, const void* f1, const void* f2, int64_t ldf1, int64_t ldf2, int64_t n,
                          int64_t k_in, const void* w, int64_t ldw, const float* bias, int64_t h, void* x, void* y, int64_t ldx,
-                         int64_t ldy, float* sim, float* probs, double threshold, uint8_t* labels_out, void* workspace,
-                         size_t workspace_bytes, ia_stream_t stream) {
+                         int64_t ldy, float* sim, float* probs, double threshold, uint8_t* labels_out, int fast_tanh,
+                         void* workspace, size_t workspace_bytes, ia_stream_t stream) {
   if (n == 0) return IA_OK;
   ProjPlan pl;
   int rc = make_plan(n, k_in, h, &pl);
@@ -489,7 +503,7 @@ int ia_project_score_fwd(int measure, int dtype, const void* f1, const void* f2,
     return IA_ERR_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  rc = project_common(measure, dtype, f1, f2, ldf1, ldf2, n, k_in, w, ldw, bias, h, x, y, ldx, ldy,
+  rc = project_common(measure, fast_tanh, dtype, f1, f2, ldf1, ldf2, n, k_in, w, ldw, bias, h, x, y, ldx, ldy,
                       reinterpret_cast<float4*>(workspace), pl, st);
   if (rc != IA_OK) return rc;
   const unsigned blocks = (unsigned)((n + 255) / 256);

@@ -305,9 +305,9 @@ def _prep_project(f1, f2, w, b):
     return f1, f2, w, b
 
 
-def project_tanh_raw(f1, f2, w, b):
+def project_tanh_raw(f1, f2, w, b, fast_tanh=False):
     """x = tanh(f1 @ w.T + b), y = tanh(f2 @ w.T + b) from ONE tcgen05 GEMM launch (reference base.py:67-75 with
-    dropout inactive); outputs in the feature dtype."""
+    dropout inactive); outputs in the feature dtype.  fast_tanh=True selects the hardware tanh.approx (2^-11 relative, opt-in)."""
     f1, f2, w, b = _prep_project(f1, f2, w, b)
     n, k = f1.shape
     h = w.shape[0]
@@ -315,11 +315,12 @@ def project_tanh_raw(f1, f2, w, b):
     y = torch.empty((n, h), dtype=f1.dtype, device=f1.device)
     with torch.cuda.device(f1.device):
         check(lib().ia_project_tanh_fwd(_DT[f1.dtype], f1.data_ptr(), f2.data_ptr(), _ld(f1), _ld(f2), n, k, w.data_ptr(), _ld(w),
-                                        b.data_ptr() if b is not None else None, h, x.data_ptr(), y.data_ptr(), h, h, _stream()))
+                                        b.data_ptr() if b is not None else None, h, x.data_ptr(), y.data_ptr(), h, h, int(bool(fast_tanh)),
+                                        _stream()))
     return x, y
 
 
-def project_score_raw(measure, f1, f2, w, b, threshold=None, want_embeds=False):
+def project_score_raw(measure, f1, f2, w, b, threshold=None, want_embeds=False, fast_tanh=False):
     """Projection + pair score in one launch (+ a [N]-sized finalize): (sim, probs, labels, x, y).  With
     want_embeds=False the embeddings never reach HBM."""
     f1, f2, w, b = _prep_project(f1, f2, w, b)
@@ -341,7 +342,8 @@ def project_score_raw(measure, f1, f2, w, b, threshold=None, want_embeds=False):
                                          _ld(w), b.data_ptr() if b is not None else None, h,
                                          x.data_ptr() if want_embeds else None, y.data_ptr() if want_embeds else None, h, h,
                                          sim.data_ptr(), probs.data_ptr(), float(threshold) if threshold is not None else 0.0,
-                                         labels.data_ptr() if labels is not None else None, ws.data_ptr(), ws.numel(), _stream()))
+                                         labels.data_ptr() if labels is not None else None, int(bool(fast_tanh)), ws.data_ptr(), ws.numel(),
+                                         _stream()))
     return sim, probs, labels, x, y
 
 
@@ -542,9 +544,9 @@ def project_tanh(f1, f2, w, b):
     return project_tanh_raw(f1, f2, w, b)
 
 
-def project_score(measure, f1, f2, w, b, threshold=None, want_embeds=False):
+def project_score(measure, f1, f2, w, b, threshold=None, want_embeds=False, fast_tanh=False):
     """Inference: projection + similarity + probability map (+ threshold labels) from the encoder features in one
     launch.  Returns (sim, probs[, labels]) or, with want_embeds, (x, y, sim, probs[, labels])."""
-    sim, probs, labels, x, y = project_score_raw(measure, f1, f2, w, b, threshold, want_embeds)
+    sim, probs, labels, x, y = project_score_raw(measure, f1, f2, w, b, threshold, want_embeds, fast_tanh)
     out = (sim, probs) if threshold is None else (sim, probs, labels)
     return ((x, y) + out) if want_embeds else out

@@ -48,6 +48,8 @@ def main():
     out["ours_project_score_tflops"] = flops / t / 1e9
     t = timed(lambda: F_.project_score_raw("cosine", f1, f2, w, b, want_embeds=True))
     out["ours_project_score_embeds_ms"] = t
+    out["ours_project_tanh_fast_ms"] = timed(lambda: F_.project_tanh_raw(f1, f2, w, b, fast_tanh=True))
+    out["ours_project_score_fast_ms"] = timed(lambda: F_.project_score_raw("cosine", f1, f2, w, b, fast_tanh=True))
 
     def lib_project():
         return torch.tanh(torch.nn.functional.linear(f1, w, bt)), torch.tanh(torch.nn.functional.linear(f2, w, bt))

@@ -164,6 +164,26 @@ def test_head_module_uses_fused_projection():
     assert head.dense.weight.grad is not None and bool(torch.isfinite(head.dense.weight.grad).all())
 
 
+def test_project_fast_tanh_is_opt_in_and_within_one_ulp():
+    """fast_tanh=True swaps in the hardware tanh.approx (2^-11 relative): outputs stay within one bf16 ulp (two fp16 ulps) of the
+    oracle, but are no longer the correctly rounded value most of the time -- which is why it is never the default."""
+    import item_alignment_b200.functional as F_
+    from oracle import torch_port
+    for dt, ulps in ((torch.bfloat16, 1.0), (torch.float16, 2.0)):
+        f1, f2, w, b = make_case(1000, 512, 384, dt, seed=77)
+        rx, ry, _, _ = torch_port.vecsim_head("cosine", f1, f2, w.float(), b)
+        args = (f1.to(DEV), f2.to(DEV), w.to(DEV), b.to(DEV))
+        xa, _ = F_.project_tanh_raw(*args)
+        xf, yf = F_.project_tanh_raw(*args, fast_tanh=True)
+        err = (xf.float().cpu() - rx).abs()
+        assert bool((err <= ulps * ulp16(rx, dt) + acc_noise(f1, w, b)).all())
+        assert not torch.equal(xa, xf)                                  # a different rounding here and there: really another path
+        check_embeddings(xa, rx, dt, "accurate path", acc_noise(f1, w, b))
+        sim_f, _ = F_.project_score("cosine", *args, fast_tanh=True)
+        ox, oy = xf.float().cpu(), yf.float().cpu()
+        parity.assert_scores_close("cosine", sim_f, torch_port.similarity("cosine", ox, oy), ox, oy, 1e-5)
+
+
 def test_project_empty_batch():
     import item_alignment_b200.functional as F_
     f = torch.zeros(0, 64, device=DEV, dtype=torch.bfloat16)
