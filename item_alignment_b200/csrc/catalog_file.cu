@@ -144,19 +144,69 @@ bool find_string_member(const char* line, size_t len, const char* key, const cha
   return false;
 }
 
-// "[0.1,-2.5e-3, ...]" -> floats.  strtof is correctly rounded, so the float32 the reference printed (repr of numpy
-// float32 = shortest round-trip decimal) comes back bit for bit.
+// One decimal number -> the double Python's float() / eval would produce, without strtod's cost (Clinger's fast path):
+// a decimal whose digit string is <= 2^53 with |exponent| <= 22 is the quotient / product of two exact doubles, i.e. the
+// correctly rounded double.  Everything else (nan, inf, > 17 digits, large exponents) goes to strtod.  The caller
+// casts to float32 -- the same decimal -> float64 -> float32 route a consumer of the reference's file takes
+// (eval at model_ensemble.py:112, then numpy's float32), so the values agree bit for bit by construction.
+// Advances *pp past the number on success.
+bool fast_decimal_to_double(const char** pp, double* out) {
+  static const double kPow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                    1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+  const char* s = *pp;
+  bool neg = false;
+  if (*s == '-') { neg = true; ++s; } else if (*s == '+') ++s;
+  uint64_t m = 0;
+  int sig = 0, exp10 = 0;
+  bool any = false;
+  while (*s >= '0' && *s <= '9') {
+    if (sig < 18) { m = m * 10 + (uint64_t)(*s - '0'); if (m) ++sig; } else return false;
+    ++s; any = true;
+  }
+  if (*s == '.') {
+    ++s;
+    while (*s >= '0' && *s <= '9') {
+      if (sig < 18) { m = m * 10 + (uint64_t)(*s - '0'); if (m) ++sig; --exp10; } else return false;
+      ++s; any = true;
+    }
+  }
+  if (!any) return false;
+  if (*s == 'e' || *s == 'E') {
+    const char* e = s + 1;
+    bool eneg = false;
+    if (*e == '-') { eneg = true; ++e; } else if (*e == '+') ++e;
+    if (!(*e >= '0' && *e <= '9')) return false;
+    int ev = 0;
+    while (*e >= '0' && *e <= '9') { if (ev < 10000) ev = ev * 10 + (*e - '0'); ++e; }
+    exp10 += eneg ? -ev : ev;
+    s = e;
+  }
+  if ((*s >= 'a' && *s <= 'z') || (*s >= 'A' && *s <= 'Z') || *s == '.') return false;   // nan, inf, hex floats, "1.2.3"
+  if (m == 0) { *out = neg ? -0.0 : 0.0; *pp = s; return true; }
+  if (m > (1ull << 53) || exp10 < -22 || exp10 > 22) return false;
+  const double q = exp10 < 0 ? (double)m / kPow10[-exp10] : (double)m * kPow10[exp10];
+  *out = neg ? -q : q;
+  *pp = s;
+  return true;
+}
+
+// "[0.1,-2.5e-3, ...]" -> floats: float32(float64(decimal)) for every value.  The float32 the reference printed (repr of a
+// numpy float32 = shortest round-trip decimal) comes back bit for bit; a float64 repr (the ensemble's averaged scores) is
+// rounded exactly like numpy rounds the evaluated Python float.
 bool parse_float_list(const char* s, size_t len, std::vector<float>* out) {
   out->clear();
-  std::string tmp(s, len);   // NUL-terminated copy for strtof
+  std::string tmp(s, len);   // NUL-terminated copy
   const char* p = tmp.c_str();
   while (*p == ' ' || *p == '[') ++p;
   while (*p && *p != ']') {
-    char* end = nullptr;
-    const float v = strtof(p, &end);
-    if (end == p) return false;
-    out->push_back(v);
-    p = end;
+    double v;
+    if (!fast_decimal_to_double(&p, &v)) {
+      char* end = nullptr;
+      v = strtod(p, &end);   // correctly rounded double for any input
+      if (end == p) return false;
+      p = end;
+    }
+    out->push_back((float)v);
     while (*p == ' ' || *p == ',') ++p;
   }
   return true;

@@ -98,6 +98,41 @@ def test_jsonl_converter_matches_reference_reader(tmp_path, side):
                 assert np.array_equal(got, want)                      # round to nearest even, like torch's .to(dtype)
 
 
+def test_jsonl_number_parsing_is_eval_then_float32_bit_for_bit(tmp_path):
+    """The native parser must give float32(float64(decimal)) -- what `eval` + numpy give a consumer of the reference's file --
+    on every kind of decimal the reference can print: shortest float32 reprs of arbitrary bit patterns (incl. subnormals and
+    the largest finite values), float64 reprs (17 digits, the ensemble's averaged scores), exponent forms, integers, signed
+    zeros, and digit strings long enough to leave the parser's fast path."""
+    import json
+    import item_alignment_b200 as ia
+    rng = np.random.default_rng(7)
+    bits = rng.integers(0, 2 ** 32, size=40000, dtype=np.uint64).astype(np.uint32)
+    f32 = bits.view(np.float32)
+    f32 = f32[np.isfinite(f32)]
+    strings = [str(v) for v in f32]                                                      # numpy's shortest round-trip float32 repr
+    f64 = np.concatenate([rng.standard_normal(5000), rng.standard_normal(2000) * 1e-30, rng.standard_normal(2000) * 1e30,
+                          np.float64(f32[:3000]) * (1 + 2.0 ** -25)])                    # near float32 rounding midpoints
+    strings += [repr(float(v)) for v in f64]
+    strings += ["0", "-0.0", "1", "-17", "1e10", "1E-10", "3.4028234663852886e+38", "1e-45", "1.401298464324817e-45", "5e-324",
+                "123456789012345678901234567890", "0.000000000000000000000000000000123456789012345678901",
+                "1.00000000000000000000000000001", "9007199254740993", "9007199254740992e3", "2.5e22", "2.5e23", "7e-23"]
+    dim = 50
+    strings += ["0.5"] * (-len(strings) % dim)
+    path = tmp_path / "numbers.jsonl"
+    with open(path, "w") as w:
+        for r in range(len(strings) // dim):
+            emb = "[" + ",".join(strings[r * dim:(r + 1) * dim]) + "]"
+            w.write(json.dumps({"src_item_id": f"row{r}", "src_item_emb": emb, "tgt_item_id": f"t{r}", "tgt_item_emb": "[0.0]",
+                                "threshold": 0.5}) + "\n")
+    with np.errstate(over="ignore"):
+        want = np.array([float(t) for t in strings], dtype=np.float64).astype(np.float32).reshape(-1, dim)
+    rows, d = ia.jsonl_to_catalog(path, tmp_path / "numbers.iacat", torch.float32, "src")
+    assert (rows, d) == want.shape
+    with ia.CatalogFile(tmp_path / "numbers.iacat") as f:
+        got = f.numpy()
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))                # bit for bit, signed zeros included
+
+
 def test_jsonl_converter_errors(tmp_path):
     import item_alignment_b200 as ia
     p = tmp_path / "ragged.jsonl"
