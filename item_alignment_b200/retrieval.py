@@ -87,6 +87,26 @@ class CatalogIndex:
         """(scores [Q,k] fp32, rows [Q,k] int64 global ids), best first; -1 / +-inf where fewer than k rows exist."""
         return unpack_keys(self.topk_keys(queries, k, measure), measure)
 
+    def topk_keys_probed(self, queries, k, measure="cosine", probe_fraction=1.0 / 32):
+        """EXPERIMENTAL (not measured yet, not used by default): the shard trick of ShardedCatalogIndex on one GPU.  g =
+        ceil(k / 16) disjoint row groups (probe_fraction of the catalog in total) are scanned first with k' = ceil(k / g)
+        <= 16 on the register top-k path; the smallest of their k'-th best keys is met or exceeded by >= k catalog rows,
+        so it seeds the thresholds of the main pass (ia_catalog_topk_seeded) and removes most of its cold-start list
+        insertions.  Same result as topk_keys by construction of the bound."""
+        rows = self.catalog.shape[0]
+        groups = max(1, -(-k // 16))
+        kp = -(-k // groups)
+        per = max(2048, int(rows * probe_fraction) // groups)
+        if k <= 16 or per * groups > rows:
+            return self.topk_keys(queries, k, measure)
+        words = None
+        for g in range(groups):
+            with CatalogIndex(self.catalog[g * per:(g + 1) * per], row_base=self.row_base + g * per) as probe:
+                pk = probe.topk_keys(queries, kp, measure)
+            w = (pk[:, kp - 1] >> 32) & 0xFFFFFFFF
+            words = w if words is None else torch.minimum(words, w)
+        return self.topk_keys(queries, k, measure, init_tau=words)
+
     def topk_dissimilarity(self, queries, k, p=2, eps=0.0, squared=None):
         """The k SMALLEST l1 / l2 dissimilarities per query with explicit eps / squaring: (dist [Q,k] ascending, rows).
         Defaults are torchkge's plain norms (torchkge/utils/dissimilarities.py:11-25: l1, l2 squared);

@@ -1,6 +1,8 @@
 """GPU parity of catalog retrieval (all-pairs + per-query top-k) through the C-ABI: exact-arithmetic golden
 fixture with engineered ties (bit-exact indices), seeded random catalogs against the stable-sort oracle with
 the gap-aware rule of tests/parity.py, shard merge == single index, and full-size properties."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -212,3 +214,17 @@ def test_two_gpu_sharded_retrieval_nccl(tmp_path):
         port = s.getsockname()[1]
     mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert [open(tmp_path / f"ok{r}").read() for r in range(2)] == ["True", "True"]
+
+
+@pytest.mark.skipif(os.environ.get("IA_EXPERIMENTAL") != "1", reason="experimental path, enable with IA_EXPERIMENTAL=1")
+def test_single_gpu_probed_topk_equals_plain_topk():
+    """CatalogIndex.topk_keys_probed (probe pass + seeded thresholds on ONE GPU) must return exactly the keys of topk_keys."""
+    import item_alignment_b200 as ia
+    gen = torch.Generator().manual_seed(31)
+    cat = torch.tanh(torch.randn(200_000, 128, generator=gen)).bfloat16()
+    cat[7000:7100] = cat[:100]
+    q = (cat[torch.randint(0, 200_000, (300,), generator=gen)].float() + 0.05 * torch.randn(300, 128, generator=gen)).bfloat16()
+    with ia.CatalogIndex(cat.to(DEV)) as index:
+        for measure in ("cosine", "inner_product"):
+            for k in (100, 40, 17):
+                assert torch.equal(index.topk_keys_probed(q.to(DEV), k, measure), index.topk_keys(q.to(DEV), k, measure))
