@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Host-side measurement for SURVEY 8f rank 4: embedding JSONL -> matrix.
-  native   ia_embedding_jsonl_to_catalog (csrc/catalog_file.cu, strtof, one pass, writes the catalog file)
+  native   ia_embedding_jsonl_to_catalog (csrc/catalog_file.cu, one pass, writes the catalog file)
   python   what a consumer of the reference's file does today: json.loads per line + eval of the embedding string
            (model_ensemble.py:112), rows stacked into a float32 matrix
 CPU only.  Usage: python scripts/bench_jsonl_converter.py [pairs] [dim]"""
