@@ -242,9 +242,10 @@ int ia_catalog_file_upload(const ia_catalog_file* f, int64_t row_begin, int64_t 
                            ia_stream_t stream);
 /* Native converter: reference JSONL -> catalog file.  side 0 = src_item_*, 1 = tgt_item_*, 2 = both;
  * an item id is stored once (first occurrence).  Values are float32(float64(decimal)) -- what eval + numpy give
- * a consumer of the reference's file, bit for bit -- then rounded to `dtype` to nearest even. */
+ * a consumer of the reference's file, bit for bit -- then rounded to `dtype` to nearest even.  `threads` workers
+ * (0 = all hardware threads) parse runs of whole lines; the output does not depend on the thread count. */
 int ia_embedding_jsonl_to_catalog(const char* jsonl_path, const char* out_path, int dtype, int side,
-                                  int64_t* rows_out, int64_t* dim_out);
+                                  int threads, int64_t* rows_out, int64_t* dim_out);
 
 #ifdef __cplusplus
 }

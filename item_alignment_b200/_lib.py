@@ -69,7 +69,8 @@ SIGNATURES = {
     "ia_catalog_file_data": (c_void_p, [c_void_p]),
     "ia_catalog_file_id": (c_void_p, [c_void_p, c_int64, ctypes.POINTER(c_int64)]),
     "ia_catalog_file_upload": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
-    "ia_embedding_jsonl_to_catalog": (c_int, [c_char_p, c_char_p, c_int, c_int, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]),
+    "ia_embedding_jsonl_to_catalog": (c_int, [c_char_p, c_char_p, c_int, c_int, c_int, ctypes.POINTER(c_int64),
+                                              ctypes.POINTER(c_int64)]),
     "ia_topk_merge": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
     "ia_unpack_keys": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "ia_pair_score_host": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_double,

@@ -40,13 +40,13 @@ def write_catalog(path, matrix, ids=None):
     check(lib().ia_catalog_file_write(os.fsencode(path), _IA_DT[m.dtype], m.data_ptr(), rows, dim, arr))
 
 
-def jsonl_to_catalog(jsonl_path, out_path, dtype=torch.bfloat16, side="both"):
-    """Reference embedding JSONL -> catalog file (native parser).  Returns (rows, dim)."""
+def jsonl_to_catalog(jsonl_path, out_path, dtype=torch.bfloat16, side="both", threads=0):
+    """Reference embedding JSONL -> catalog file (native parser, `threads` workers, 0 = all cores).  Returns (rows, dim)."""
     if side not in _SIDES:
         raise ValueError("side must be 'src', 'tgt' or 'both'")
     rows, dim = ctypes.c_int64(0), ctypes.c_int64(0)
     check(lib().ia_embedding_jsonl_to_catalog(os.fsencode(jsonl_path), os.fsencode(out_path), _IA_DT[dtype], _SIDES[side],
-                                              ctypes.byref(rows), ctypes.byref(dim)))
+                                              int(threads), ctypes.byref(rows), ctypes.byref(dim)))
     return rows.value, dim.value
 
 

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -336,50 +337,128 @@ int ia_catalog_file_upload(const ia_catalog_file* f, int64_t row_begin, int64_t 
 
 // Reference embedding JSONL (finetune_text.py:784-792) -> catalog file.  side: 0 = src_item_*, 1 = tgt_item_*, 2 = both.
 // An item that occurs in several pairs is stored once (first occurrence wins, like a dict built in file order).
-int ia_embedding_jsonl_to_catalog(const char* jsonl_path, const char* out_path, int dtype, int side, int64_t* rows_out,
-                                  int64_t* dim_out) {
-  if (jsonl_path == nullptr || out_path == nullptr || side < 0 || side > 2) { set_error("jsonl: bad arguments"); return IA_ERR_INVALID; }
+// The file is mmap'ed and parsed in blocks by `threads` workers (0 = all hardware threads), each on a run of whole lines;
+// the blocks' records are then appended in file order by one thread, so the output does not depend on the thread count.
+int ia_embedding_jsonl_to_catalog(const char* jsonl_path, const char* out_path, int dtype, int side, int threads,
+                                  int64_t* rows_out, int64_t* dim_out) {
+  if (jsonl_path == nullptr || out_path == nullptr || side < 0 || side > 2 || threads < 0) { set_error("jsonl: bad arguments"); return IA_ERR_INVALID; }
   if (dtype != IA_F32 && dtype != IA_BF16 && dtype != IA_F16) { set_error("jsonl: unsupported dtype %d", dtype); return IA_ERR_UNSUPPORTED; }
-  FILE* in = fopen(jsonl_path, "r");
-  if (in == nullptr) { set_error("cannot open %s: %s", jsonl_path, strerror(errno)); return IA_ERR_INVALID; }
+  const int fd = ::open(jsonl_path, O_RDONLY);
+  if (fd < 0) { set_error("cannot open %s: %s", jsonl_path, strerror(errno)); return IA_ERR_INVALID; }
+  struct stat st;
+  if (fstat(fd, &st) != 0) { ::close(fd); set_error("cannot stat %s: %s", jsonl_path, strerror(errno)); return IA_ERR_INVALID; }
+  const size_t size = (size_t)st.st_size;
+  const char* data = nullptr;
+  if (size > 0) {
+    void* map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (map == MAP_FAILED) { ::close(fd); set_error("mmap of %s failed: %s", jsonl_path, strerror(errno)); return IA_ERR_CUDA; }
+    data = static_cast<const char*>(map);
+    madvise(map, size, MADV_SEQUENTIAL);
+  }
+  struct Unmap {
+    const char* d; size_t n; int fd;
+    ~Unmap() { if (d) munmap(const_cast<char*>(d), n); ::close(fd); }
+  } unmap{data, size, fd};
+
   Writer w;
   int rc = w.open_file(out_path, dtype, true);
-  if (rc != IA_OK) { fclose(in); return rc; }
-  std::unordered_map<std::string, uint64_t> seen;
-  std::vector<float> vals;
-  char* line = nullptr;
-  size_t cap = 0;
-  ssize_t len;
-  int64_t line_no = 0;
+  if (rc != IA_OK) return rc;
+  int nthreads = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 64) nthreads = 64;
+
+  struct Chunk {   // what one worker extracts from its run of lines, in line order
+    std::string ids;                 // ids back to back
+    std::vector<uint32_t> id_len;    // one entry per record
+    std::vector<float> vals;         // dim floats per record
+    std::vector<uint32_t> dims;      // values in each record (all equal in a well-formed file)
+    int64_t lines = 0;               // lines consumed (for error messages)
+    int64_t err_line = -1;           // first bad line within the chunk, 1-based
+    std::string err;
+  };
   static const char* kId[2] = {"src_item_id", "tgt_item_id"};
   static const char* kEmb[2] = {"src_item_emb", "tgt_item_emb"};
-  while (rc == IA_OK && (len = getline(&line, &cap, in)) >= 0) {
-    ++line_no;
-    bool blank = true;
-    for (ssize_t i = 0; i < len; ++i) if (line[i] != ' ' && line[i] != '\n' && line[i] != '\r' && line[i] != '\t') { blank = false; break; }
-    if (blank) continue;
-    for (int sd = 0; sd < 2 && rc == IA_OK; ++sd) {
-      if (side != 2 && side != sd) continue;
-      const char *id, *emb;
-      size_t id_len, emb_len;
-      if (!find_string_member(line, (size_t)len, kId[sd], &id, &id_len) || !find_string_member(line, (size_t)len, kEmb[sd], &emb, &emb_len)) {
-        set_error("%s:%lld: missing %s / %s", jsonl_path, (long long)line_no, kId[sd], kEmb[sd]);
-        rc = IA_ERR_INVALID;
-        break;
+  auto parse_range = [&](const char* p, const char* end, Chunk* c) {
+    std::vector<float> vals;
+    while (p < end) {
+      const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
+      const char* le = nl ? nl : end;
+      const size_t len = (size_t)(le - p);
+      ++c->lines;
+      bool blank = true;
+      for (size_t i = 0; i < len; ++i) if (p[i] != ' ' && p[i] != '\r' && p[i] != '\t') { blank = false; break; }
+      if (!blank) {
+        for (int sd = 0; sd < 2; ++sd) {
+          if (side != 2 && side != sd) continue;
+          const char *id, *emb;
+          size_t idl, embl;
+          if (!find_string_member(p, len, kId[sd], &id, &idl) || !find_string_member(p, len, kEmb[sd], &emb, &embl)) {
+            c->err_line = c->lines; c->err = std::string("missing ") + kId[sd] + " / " + kEmb[sd];
+            return;
+          }
+          if (!parse_float_list(emb, embl, &vals) || vals.empty()) {
+            c->err_line = c->lines; c->err = std::string(kEmb[sd]) + " is not a float list";
+            return;
+          }
+          c->ids.append(id, idl);
+          c->id_len.push_back((uint32_t)idl);
+          c->vals.insert(c->vals.end(), vals.begin(), vals.end());
+          c->dims.push_back((uint32_t)vals.size());
+        }
       }
-      std::string key(id, id_len);
-      if (seen.count(key)) continue;
-      if (!parse_float_list(emb, emb_len, &vals) || vals.empty()) {
-        set_error("%s:%lld: %s is not a float list", jsonl_path, (long long)line_no, kEmb[sd]);
-        rc = IA_ERR_INVALID;
-        break;
-      }
-      seen.emplace(std::move(key), w.rows);
-      rc = w.add_row(vals.data(), vals.size(), id, id_len);
+      p = nl ? nl + 1 : end;
     }
+  };
+
+  std::unordered_map<std::string, uint64_t> seen;
+  // bytes of text per worker and block: an even share of the file, at most 32 MiB (bounds the memory held before the merge)
+  size_t per_worker = (size + (size_t)nthreads - 1) / (size_t)nthreads;
+  if (per_worker < (64u << 10)) per_worker = 64u << 10;
+  if (per_worker > (32u << 20)) per_worker = 32u << 20;
+  size_t pos = 0;
+  int64_t lines_before = 0;
+  while (pos < size && rc == IA_OK) {
+    // cut [pos, block_end) into nthreads runs of whole lines
+    std::vector<const char*> cuts;
+    cuts.push_back(data + pos);
+    for (int t = 1; t <= nthreads; ++t) {
+      size_t target = pos + (size_t)t * per_worker;
+      const char* cut = data + size;
+      if (target < size) {
+        const char* nl = static_cast<const char*>(memchr(data + target, '\n', size - target));
+        cut = nl ? nl + 1 : data + size;
+      }
+      if (cut < cuts.back()) cut = cuts.back();
+      cuts.push_back(cut);
+      if (cut == data + size) break;
+    }
+    const int nchunks = (int)cuts.size() - 1;
+    std::vector<Chunk> chunks((size_t)nchunks);
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nchunks; ++t) pool.emplace_back(parse_range, cuts[t], cuts[t + 1], &chunks[t]);
+    parse_range(cuts[0], cuts[1], &chunks[0]);
+    for (auto& th : pool) th.join();
+    // append in file order; the first error in file order wins
+    for (int t = 0; t < nchunks && rc == IA_OK; ++t) {
+      Chunk& c = chunks[t];
+      size_t id_pos = 0, val_pos = 0;
+      for (size_t r = 0; r < c.id_len.size() && rc == IA_OK; ++r) {
+        std::string key(c.ids.data() + id_pos, c.id_len[r]);
+        if (!seen.count(key)) {
+          rc = w.add_row(c.vals.data() + val_pos, c.dims[r], key.data(), key.size());
+          seen.emplace(std::move(key), w.rows);
+        }
+        id_pos += c.id_len[r];
+        val_pos += c.dims[r];
+      }
+      if (rc == IA_OK && c.err_line >= 0) {
+        set_error("%s:%lld: %s", jsonl_path, (long long)(lines_before + c.err_line), c.err.c_str());
+        rc = IA_ERR_INVALID;
+      }
+      lines_before += c.lines;
+    }
+    pos = (size_t)(cuts.back() - data);
   }
-  free(line);
-  fclose(in);
   if (rc != IA_OK) return rc;
   if ((rc = w.finish()) != IA_OK) return rc;
   if (rows_out) *rows_out = (int64_t)w.rows;

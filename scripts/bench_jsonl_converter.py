@@ -29,8 +29,12 @@ with tempfile.TemporaryDirectory() as td:
             w.write(torch_port.embedding_jsonl_record(f"s{i:031d}", f"t{i:031d}", a, b, 0.5))
     size = os.path.getsize(src)
     t0 = time.perf_counter()
-    rows, d = ia.jsonl_to_catalog(src, os.path.join(td, "c.iacat"), torch.bfloat16, "both")
+    rows, d = ia.jsonl_to_catalog(src, os.path.join(td, "c.iacat"), torch.bfloat16, "both", threads=1)
     t_native = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ia.jsonl_to_catalog(src, os.path.join(td, "c_mt.iacat"), torch.bfloat16, "both", threads=0)
+    t_native_mt = time.perf_counter() - t0
+    same_mt = open(os.path.join(td, "c.iacat"), "rb").read() == open(os.path.join(td, "c_mt.iacat"), "rb").read()
     t0 = time.perf_counter()
     ids, mats = [], []
     with open(src) as r:
@@ -44,4 +48,6 @@ with tempfile.TemporaryDirectory() as td:
     with ia.CatalogFile(os.path.join(td, "c.iacat")) as f:
         same = np.array_equal(f.numpy(), torch.from_numpy(mat).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16))
     print(json.dumps({"file_mb": size / 1e6, "rows": rows, "dim": d, "native_s": t_native, "native_mb_per_s": size / 1e6 / t_native,
+                      "native_all_cores_s": t_native_mt, "native_all_cores_mb_per_s": size / 1e6 / t_native_mt, "cores": os.cpu_count(),
+                      "all_cores_output_identical": bool(same_mt),
                       "python_eval_s": t_py, "python_mb_per_s": size / 1e6 / t_py, "speedup": t_py / t_native, "identical": bool(same)}))

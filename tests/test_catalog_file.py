@@ -133,6 +133,36 @@ def test_jsonl_number_parsing_is_eval_then_float32_bit_for_bit(tmp_path):
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))                # bit for bit, signed zeros included
 
 
+def test_jsonl_converter_output_does_not_depend_on_the_thread_count(tmp_path):
+    import item_alignment_b200 as ia
+    src = tmp_path / "embeds.jsonl"
+    rng = np.random.default_rng(11)
+    items = [np.tanh(rng.standard_normal(96)).astype(np.float32) for _ in range(300)]
+    with open(src, "w") as w:                                     # ~1.3 MB: several 64 KiB worker runs; ids repeat across runs
+        for i in range(600):
+            a, b = int(rng.integers(0, 300)), int(rng.integers(0, 300))
+            w.write(torch_port.embedding_jsonl_record(f"id{a}", f"id{b}", items[a], items[b], 0.5))
+            if i % 97 == 0:
+                w.write("\n")
+    ids, mat = torch_port.read_embedding_jsonl(src, "both")
+    outs = []
+    for t in (1, 2, 5, 16, 0):
+        out = tmp_path / f"t{t}.iacat"
+        assert ia.jsonl_to_catalog(src, out, torch.float32, "both", threads=t) == mat.shape
+        outs.append(out.read_bytes())
+    assert all(o == outs[0] for o in outs)
+    with ia.CatalogFile(tmp_path / "t5.iacat") as f:
+        assert np.array_equal(f.numpy(), mat) and [f.id(i) for i in range(f.rows)] == ids
+    # a bad line deep in the file is reported with its line number whatever the thread count
+    lines = src.read_text().splitlines(keepends=True)
+    lines[450] = '{"src_item_id": "x", "src_item_emb": "[oops]", "tgt_item_id": "y", "tgt_item_emb": "[1.0]"}\n'
+    bad = tmp_path / "bad.jsonl"
+    bad.write_text("".join(lines))
+    for t in (1, 7):
+        with pytest.raises(ValueError, match=r"bad\.jsonl:451: src_item_emb is not a float list"):
+            ia.jsonl_to_catalog(bad, tmp_path / "bad.iacat", torch.float32, "both", threads=t)
+
+
 def test_jsonl_converter_errors(tmp_path):
     import item_alignment_b200 as ia
     p = tmp_path / "ragged.jsonl"
