@@ -69,14 +69,20 @@ int ia_pair_score_fwd(int measure, int dtype, const void* x, const void* y, int6
  *   loss_out  : 1 float (mean / sum) or n floats (IA_RED_NONE)
  *   dx, dy    : [n, d] gradients in grad_dtype (= dtype, or IA_F32), leading dims lddx / lddy;
  *               both NULL -> forward + loss only
- *   grad_scale: upstream d(total)/d(loss) folded into dx, dy (1.0 for a plain loss.backward())
+ *   grad_scale: upstream d(total)/d(loss) known on the HOST, folded into dx, dy (1.0 for a plain loss.backward())
+ *   upstream_dev: NULL, or a DEVICE float with the upstream scalar autograd hands to backward() (GradScaler's 65536
+ *               under --fp16, 1/accumulation_steps, ...: finetune_text.py:479-482 scales the loss before backward()).
+ *               It multiplies grad_scale BEFORE the single rounding to grad_dtype, as the reference's fp32 backward does,
+ *               so 16-bit gradients neither underflow nor round twice.  With skip_if_one != 0 the launch is a device-side
+ *               no-op when *upstream_dev == 1 (the gradients a previous forward wrote are already exact) -- no host sync.
+ *               With upstream_dev, loss_out may be NULL (mean / sum reductions: gradients only).
  *   sim, probs may be NULL. */
 int ia_pair_score_loss_fwd_bwd(int measure, int loss, float margin, int reduction, int dtype,
                                int grad_dtype, const void* x, const void* y, int64_t ldx, int64_t ldy,
                                const int64_t* labels, int64_t n, int64_t d, float* sim, float* probs,
                                float* loss_out, void* dx, void* dy, int64_t lddx, int64_t lddy,
-                               float grad_scale, void* workspace, size_t workspace_bytes,
-                               ia_stream_t stream);
+                               float grad_scale, const float* upstream_dev, int skip_if_one, void* workspace,
+                               size_t workspace_bytes, ia_stream_t stream);
 
 /* ---- backward of the score alone (upstream gradient is an arbitrary per-pair vector) ----------
  * Replaces autograd of InnerProduct / CosineSimilarity / PairwiseDistance when the caller keeps the
@@ -89,13 +95,16 @@ int ia_pair_score_bwd(int measure, int dtype, int grad_dtype, const void* x, con
  * Replaces the per-pair Python loop of GCNTwoTower.forward (src/models/graph.py:87-117: one head call per pair,
  * torch.cat per iteration) and scores id pairs (item_train_pair.jsonl) straight against an embedding matrix such
  * as pred_text.py:158-192's feature_matrix.  ex and ey may be the same matrix.  Gradients come back dense per pair
- * ([n, d]); the caller scatters them into the embedding matrix gradient (index_add). */
+ * ([n, d]); the caller scatters them into the embedding matrix gradient (index_add).
+ * rows_x / rows_y are the row counts of ex / ey: an index outside [0, rows) never reads out of bounds -- that pair's
+ * sim / probs / loss contribution / gradients become NaN (torch indexing in the reference loop would raise). */
 int ia_pair_score_gather_fwd(int measure, int dtype, const void* ex, const void* ey, int64_t rows_x,
                              int64_t rows_y, int64_t ldx, int64_t ldy, const int64_t* xi, const int64_t* yi,
                              int64_t n, int64_t d, float* sim, float* probs, double threshold,
                              uint8_t* labels_out, ia_stream_t stream);
 int ia_pair_score_gather_loss_fwd_bwd(int measure, int loss, float margin, int reduction, int dtype,
-                                      int grad_dtype, const void* ex, const void* ey, int64_t ldx, int64_t ldy,
+                                      int grad_dtype, const void* ex, const void* ey, int64_t rows_x,
+                                      int64_t rows_y, int64_t ldx, int64_t ldy,
                                       const int64_t* xi, const int64_t* yi, const int64_t* labels, int64_t n,
                                       int64_t d, float* sim, float* probs, float* loss_out, void* dx, void* dy,
                                       int64_t lddx, int64_t lddy, float grad_scale, void* workspace,
@@ -120,14 +129,17 @@ int ia_score_loss_fwd_bwd(int loss, float margin, int reduction, const float* si
  * logits = [x ; y] . W^T + b with W [2, 2h] fp32 row-major, probs = softmax(logits) (numpy twin:
  * submit/similarity.py:19-24).  labels NULL -> forward only.  With labels: loss (mean CE,
  * text.py:1408-1409,1473) and, when non-NULL, dx, dy (grad_dtype), dW [2,2h], db [2] (fp32).
+ * upstream_dev / skip_if_one: as in ia_pair_score_loss_fwd_bwd (device-resident upstream scalar folded into every
+ * gradient before rounding; optional device-side no-op when it is 1; loss_out may then be NULL).
+ * Labels must be 0 or 1 (any non-zero value counts as class 1; nn.CrossEntropyLoss's ignore_index is not offered).
  * workspace: ia_softmax_head_workspace_bytes(h). */
 size_t ia_softmax_head_workspace_bytes(int64_t h);
 int ia_softmax_head_fwd_bwd(int dtype, int grad_dtype, const void* x, const void* y, int64_t ldx,
                             int64_t ldy, const float* w, const float* b, const int64_t* labels,
                             int64_t n, int64_t h, float* logits, float* probs, float* loss_out,
                             void* dx, void* dy, int64_t lddx, int64_t lddy, float* dw, float* db,
-                            float grad_scale, void* workspace, size_t workspace_bytes,
-                            ia_stream_t stream);
+                            float grad_scale, const float* upstream_dev, int skip_if_one, void* workspace,
+                            size_t workspace_bytes, ia_stream_t stream);
 
 /* ---- in-place scale of gradients by a device scalar (autograd upstream != 1, e.g. GradScaler) --
  * No-op on the device when *g == 1.0f. */

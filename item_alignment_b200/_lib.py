@@ -30,13 +30,13 @@ SIGNATURES = {
                                   c_void_p, c_double, c_void_p, c_void_p]),
     "ia_pair_score_loss_fwd_bwd": (c_int, [c_int, c_int, c_float, c_int, c_int, c_int, c_void_p, c_void_p, c_int64,
                                            c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
-                                           c_void_p, c_int64, c_int64, c_float, c_void_p, c_size_t, c_void_p]),
+                                           c_void_p, c_int64, c_int64, c_float, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "ia_pair_score_bwd": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
                                   c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "ia_pair_score_gather_fwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                          c_int64, c_int64, c_void_p, c_void_p, c_double, c_void_p, c_void_p]),
     "ia_pair_score_gather_loss_fwd_bwd": (c_int, [c_int, c_int, c_float, c_int, c_int, c_int, c_void_p, c_void_p, c_int64, c_int64,
-                                                  c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                                  c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                                   c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_size_t, c_void_p]),
     "ia_threshold_sweep": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "ia_score_loss_fwd_bwd": (c_int, [c_int, c_float, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_float,
@@ -44,7 +44,7 @@ SIGNATURES = {
     "ia_softmax_head_workspace_bytes": (c_size_t, [c_int64]),
     "ia_softmax_head_fwd_bwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                         c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
-                                        c_int64, c_void_p, c_void_p, c_float, c_void_p, c_size_t, c_void_p]),
+                                        c_int64, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "ia_scale_inplace": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "ia_project_tanh_fwd": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p,
                                     c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),

@@ -204,8 +204,8 @@ int ia_pair_score_fwd(int measure, int dtype, const void* x, const void* y, int6
 int ia_pair_score_loss_fwd_bwd(int measure, int loss, float margin, int reduction, int dtype, int grad_dtype,
                                const void* x, const void* y, int64_t ldx, int64_t ldy, const int64_t* labels,
                                int64_t n, int64_t d, float* sim, float* probs, float* loss_out, void* dx, void* dy,
-                               int64_t lddx, int64_t lddy, float grad_scale, void* workspace,
-                               size_t workspace_bytes, ia_stream_t stream) {
+                               int64_t lddx, int64_t lddy, float grad_scale, const float* upstream_dev,
+                               int skip_if_one, void* workspace, size_t workspace_bytes, ia_stream_t stream) {
   int rc = check_common(measure, dtype, x, y, n, d, ldx, ldy);
   if (rc != IA_OK) return rc;
   if (loss < IA_LOSS_BCE || loss > IA_LOSS_COSINE) { set_error("unsupported loss_type %d", loss); return IA_ERR_INVALID; }
@@ -213,16 +213,20 @@ int ia_pair_score_loss_fwd_bwd(int measure, int loss, float margin, int reductio
   if (grad_dtype != dtype && grad_dtype != IA_F32) { set_error("grad_dtype must equal dtype or be fp32"); return IA_ERR_UNSUPPORTED; }
   if ((dx == nullptr) != (dy == nullptr)) { set_error("dx and dy must both be given or both be NULL"); return IA_ERR_INVALID; }
   if (dx != nullptr && (lddx < d || lddy < d)) { set_error("bad gradient leading dimension"); return IA_ERR_INVALID; }
-  if (loss_out == nullptr || (n > 0 && labels == nullptr)) { set_error("loss_out / labels must not be NULL"); return IA_ERR_INVALID; }
-  if (reduction != IA_RED_NONE && (workspace == nullptr || workspace_bytes < kWorkspaceBytes)) {
-    set_error("workspace too small: need %zu bytes", kWorkspaceBytes);
-    return IA_ERR_WORKSPACE;
+  if (n > 0 && labels == nullptr) { set_error("labels must not be NULL"); return IA_ERR_INVALID; }
+  if (workspace == nullptr || workspace_bytes < kWorkspaceBytes) {
+    if (reduction != IA_RED_NONE || loss_out == nullptr) { set_error("workspace too small: need %zu bytes", kWorkspaceBytes); return IA_ERR_WORKSPACE; }
+  }
+  if (loss_out == nullptr) {
+    // gradient recomputation (autograd backward): the loss value is not wanted, it lands in the workspace header
+    if (upstream_dev == nullptr || reduction == IA_RED_NONE) { set_error("loss_out may only be NULL with upstream_dev and mean / sum reduction"); return IA_ERR_INVALID; }
+    loss_out = reinterpret_cast<float*>(static_cast<char*>(workspace) + kWorkspaceScratchOffset);
   }
   if (n == 0) {
     // torch: mean over an empty batch is nan, sum is 0
     if (reduction != IA_RED_NONE) {
-      const float v = reduction == IA_RED_MEAN ? __builtin_nanf("") : 0.f;
-      IA_CUDA_CHECK(cudaMemcpyAsync(loss_out, &v, sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+      static const float kEmpty[2] = {__builtin_nanf(""), 0.f};   // static storage: the async copy may outlive this frame
+      IA_CUDA_CHECK(cudaMemcpyAsync(loss_out, &kEmpty[reduction == IA_RED_MEAN ? 0 : 1], sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
     }
     return IA_OK;
   }
@@ -233,6 +237,7 @@ int ia_pair_score_loss_fwd_bwd(int measure, int loss, float margin, int reductio
   p.loss_scale = reduction == IA_RED_MEAN ? 1.0 / (double)n : 1.0;
   p.grad_scale = reduction == IA_RED_MEAN ? (float)((double)grad_scale / (double)n) : grad_scale;
   p.workspace = workspace;
+  p.upstream = upstream_dev; p.upstream_skip_one = skip_if_one;
   return dispatch_pair(kModeFused, loss == IA_LOSS_COSINE, measure, dtype, grad_dtype, p, (cudaStream_t)stream);
 }
 
@@ -259,13 +264,15 @@ int ia_pair_score_gather_fwd(int measure, int dtype, const void* ex, const void*
   if (n == 0) return IA_OK;
   PairParams p{};
   p.x = ex; p.y = ey; p.ldx = ldx; p.ldy = ldy; p.xi = xi; p.yi = yi; p.n = n; p.d = (int)d;
+  p.rows_x = rows_x; p.rows_y = rows_y;
   p.sim = sim; p.probs = probs; p.labels_out = labels_out; p.threshold = threshold;
   return dispatch_pair(kModeFwd, false, measure, dtype, dtype, p, (cudaStream_t)stream);
 }
 
 int ia_pair_score_gather_loss_fwd_bwd(int measure, int loss, float margin, int reduction, int dtype, int grad_dtype,
-                                      const void* ex, const void* ey, int64_t ldx, int64_t ldy, const int64_t* xi,
-                                      const int64_t* yi, const int64_t* labels, int64_t n, int64_t d, float* sim,
+                                      const void* ex, const void* ey, int64_t rows_x, int64_t rows_y, int64_t ldx,
+                                      int64_t ldy, const int64_t* xi, const int64_t* yi, const int64_t* labels, int64_t n,
+                                      int64_t d, float* sim,
                                       float* probs, float* loss_out, void* dx, void* dy, int64_t lddx, int64_t lddy,
                                       float grad_scale, void* workspace, size_t workspace_bytes, ia_stream_t stream) {
   int rc = check_common(measure, dtype, ex, ey, n, d, ldx, ldy);
@@ -274,15 +281,19 @@ int ia_pair_score_gather_loss_fwd_bwd(int measure, int loss, float margin, int r
   if (reduction != IA_RED_MEAN && reduction != IA_RED_SUM) { set_error("gather entry point supports mean / sum reduction"); return IA_ERR_INVALID; }
   if (grad_dtype != dtype && grad_dtype != IA_F32) { set_error("grad_dtype must equal dtype or be fp32"); return IA_ERR_UNSUPPORTED; }
   if ((dx == nullptr) != (dy == nullptr)) { set_error("dx and dy must both be given or both be NULL"); return IA_ERR_INVALID; }
-  if (loss_out == nullptr || (n > 0 && (labels == nullptr || xi == nullptr || yi == nullptr))) { set_error("loss_out / labels / indices must not be NULL"); return IA_ERR_INVALID; }
+  if (loss_out == nullptr || (n > 0 && (labels == nullptr || xi == nullptr || yi == nullptr || rows_x <= 0 || rows_y <= 0))) {
+    set_error("loss_out / labels / indices must not be NULL and the row counts must be positive");
+    return IA_ERR_INVALID;
+  }
   if (workspace == nullptr || workspace_bytes < kWorkspaceBytes) { set_error("workspace too small: need %zu bytes", kWorkspaceBytes); return IA_ERR_WORKSPACE; }
   if (n == 0) {
-    const float v = reduction == IA_RED_MEAN ? __builtin_nanf("") : 0.f;
-    IA_CUDA_CHECK(cudaMemcpyAsync(loss_out, &v, sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    static const float kEmpty[2] = {__builtin_nanf(""), 0.f};
+    IA_CUDA_CHECK(cudaMemcpyAsync(loss_out, &kEmpty[reduction == IA_RED_MEAN ? 0 : 1], sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
     return IA_OK;
   }
   PairParams p{};
   p.x = ex; p.y = ey; p.ldx = ldx; p.ldy = ldy; p.xi = xi; p.yi = yi; p.labels = labels; p.n = n; p.d = (int)d;
+  p.rows_x = rows_x; p.rows_y = rows_y;
   p.sim = sim; p.probs = probs; p.loss_out = loss_out; p.dx = dx; p.dy = dy; p.lddx = lddx; p.lddy = lddy;
   p.loss = loss; p.margin = margin; p.reduction = reduction;
   p.loss_scale = reduction == IA_RED_MEAN ? 1.0 / (double)n : 1.0;
@@ -319,8 +330,8 @@ int ia_score_loss_fwd_bwd(int loss, float margin, int reduction, const float* si
   }
   if (n == 0) {
     if (reduction != IA_RED_NONE) {
-      const float v = reduction == IA_RED_MEAN ? __builtin_nanf("") : 0.f;
-      IA_CUDA_CHECK(cudaMemcpyAsync(loss_out, &v, sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+      static const float kEmpty[2] = {__builtin_nanf(""), 0.f};
+      IA_CUDA_CHECK(cudaMemcpyAsync(loss_out, &kEmpty[reduction == IA_RED_MEAN ? 0 : 1], sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
     }
     return IA_OK;
   }

@@ -254,16 +254,26 @@ int ia_catalog_file_open(const char* path, ia_catalog_file** out) {
   memcpy(&f->hdr, map, sizeof(FileHeader));
   const FileHeader& h = f->hdr;
   const bool dtype_ok = h.dtype == IA_F32 || h.dtype == IA_BF16 || h.dtype == IA_F16;
-  const uint64_t data_bytes = dtype_ok ? h.rows * h.dim * elem_bytes((int)h.dtype) : 0;
-  bool ok = memcmp(h.magic, kMagic, 8) == 0 && h.version == 1 && dtype_ok && h.dim > 0 && h.data_offset >= sizeof(FileHeader) &&
-            h.data_offset % 16 == 0 && h.data_offset + data_bytes <= (uint64_t)st.st_size;
+  // every size below comes from the file: overflow-checked arithmetic, then bounds against the mapped size
+  const uint64_t fsize = (uint64_t)st.st_size;
+  uint64_t data_bytes = 0, data_end = 0, elems = 0;
+  bool ok = memcmp(h.magic, kMagic, 8) == 0 && h.version == 1 && dtype_ok && h.dim > 0 && h.rows <= (uint64_t)INT64_MAX &&
+            h.dim <= (uint64_t)INT64_MAX && h.data_offset >= sizeof(FileHeader) && h.data_offset % 16 == 0 &&
+            !__builtin_mul_overflow(h.rows, h.dim, &elems) &&
+            !__builtin_mul_overflow(elems, (uint64_t)elem_bytes((int)h.dtype), &data_bytes) &&
+            !__builtin_add_overflow(h.data_offset, data_bytes, &data_end) && data_end <= fsize;
   if (ok && h.ids_offset != 0) {
-    ok = h.ids_offset % 8 == 0 && h.ids_offset >= h.data_offset + data_bytes && h.ids_offset + h.ids_bytes <= (uint64_t)st.st_size &&
-         h.ids_bytes >= (h.rows + 1) * 8;
+    uint64_t ids_end = 0, table_bytes = 0;
+    ok = h.ids_offset % 8 == 0 && h.ids_offset >= data_end && !__builtin_add_overflow(h.ids_offset, h.ids_bytes, &ids_end) &&
+         ids_end <= fsize && !__builtin_mul_overflow(h.rows + 1, (uint64_t)8, &table_bytes) && h.ids_bytes >= table_bytes;
     if (ok) {
       f->id_off = reinterpret_cast<const uint64_t*>(static_cast<const char*>(map) + h.ids_offset);
       f->id_blob = reinterpret_cast<const char*>(f->id_off + h.rows + 1);
-      ok = f->id_off[0] == 0 && (h.rows + 1) * 8 + f->id_off[h.rows] == h.ids_bytes;
+      const uint64_t blob_bytes = h.ids_bytes - table_bytes;
+      ok = f->id_off[0] == 0 && f->id_off[h.rows] == blob_bytes;
+      // the offset table must be non-decreasing (with the end fixed above that bounds every entry by the blob size):
+      // ia_catalog_file_id hands out blob + off[row] with length off[row+1] - off[row]
+      for (uint64_t i = 0; ok && i < h.rows; ++i) ok = f->id_off[i] <= f->id_off[i + 1];
     }
   }
   if (!ok) {

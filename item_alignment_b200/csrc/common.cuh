@@ -46,6 +46,7 @@ int blocks_per_sm(K kernel, int threads, size_t smem = 0) {
 // workspace layout shared by the fused kernels: [counter u32 | pad to 64 B | double partials[]]
 constexpr int kMaxPartials = 8192;
 constexpr size_t kWorkspaceBytes = 64 + sizeof(double) * kMaxPartials;
+constexpr size_t kWorkspaceScratchOffset = 16;   // one float of the header: where an unwanted loss value goes (gradient recomputation)
 
 // ----------------------------------------------------------------------------- device side
 constexpr float kCosEps = 1e-8f;      // nn.CosineSimilarity eps (reference base.py:58)

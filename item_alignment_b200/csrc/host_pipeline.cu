@@ -63,6 +63,24 @@ static int ensure(Lane& l, size_t in_bytes, size_t grad_bytes, size_t rows) {
   return IA_OK;
 }
 
+// The entry points run on `device` and hand the caller's current device back on EVERY exit path; on an error exit the lanes
+// are drained first, so no asynchronous copy is still writing into the caller's buffers after the call has returned.
+struct DeviceScope {
+  int prev = -1;
+  HostCtx* ctx = nullptr;
+  bool ok = true;
+  explicit DeviceScope(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceScope() {
+    if (ctx != nullptr)
+      for (int i = 0; i < kStreams; ++i)
+        if (ctx->lanes[i].stream != nullptr) cudaStreamSynchronize(ctx->lanes[i].stream);
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 static int64_t chunk_rows_for(int64_t n, int64_t row_bytes) {
   int64_t rows = (16ll << 20) / (row_bytes > 0 ? row_bytes : 1);   // ~16 MiB of x per chunk
   if (rows < 1024) rows = 1024;
@@ -81,9 +99,11 @@ int ia_pair_score_host(int measure, int dtype, const void* x, const void* y, int
   if (device < 0 || device >= 16) { set_error("bad device %d", device); return IA_ERR_INVALID; }
   if (n < 0 || d <= 0 || (n > 0 && (x == nullptr || y == nullptr))) { set_error("bad arguments"); return IA_ERR_INVALID; }
   if (n == 0) return IA_OK;
-  IA_CUDA_CHECK(cudaSetDevice(device));
   HostCtx& ctx = g_ctx[device];
   std::lock_guard<std::mutex> lock(ctx.mu);
+  DeviceScope scope(device);
+  if (!scope.ok) { set_error("cudaSetDevice(%d) failed", device); return IA_ERR_CUDA; }
+  scope.ctx = &ctx;
   const size_t es = dtype == IA_F32 ? 4 : 2;
   const int64_t row_bytes = d * (int64_t)es;
   const int64_t chunk = chunk_rows_for(n, row_bytes);
@@ -120,9 +140,11 @@ int ia_pair_score_loss_host(int measure, int loss, float margin, int reduction, 
   if (reduction != IA_RED_MEAN && reduction != IA_RED_SUM) { set_error("host entry point supports mean / sum reduction"); return IA_ERR_INVALID; }
   if ((dx == nullptr) != (dy == nullptr)) { set_error("dx and dy must both be given or both be NULL"); return IA_ERR_INVALID; }
   if (n == 0) { *loss_out = reduction == IA_RED_MEAN ? __builtin_nanf("") : 0.f; return IA_OK; }
-  IA_CUDA_CHECK(cudaSetDevice(device));
   HostCtx& ctx = g_ctx[device];
   std::lock_guard<std::mutex> lock(ctx.mu);
+  DeviceScope scope(device);
+  if (!scope.ok) { set_error("cudaSetDevice(%d) failed", device); return IA_ERR_CUDA; }
+  scope.ctx = &ctx;
   const size_t es = dtype == IA_F32 ? 4 : 2;
   const int64_t row_bytes = d * (int64_t)es;
   const int64_t chunk = chunk_rows_for(n, row_bytes);
@@ -145,7 +167,7 @@ int ia_pair_score_loss_host(int measure, int loss, float margin, int reduction, 
     float* lslot = l.loss + (ci / kStreams) % 4096;
     rc = ia_pair_score_loss_fwd_bwd(measure, loss, margin, IA_RED_SUM, dtype, dtype, l.x, l.y, d, d, l.labels, rows, d,
                                     nullptr, nullptr, lslot, dx ? l.dx : nullptr, dx ? l.dy : nullptr, d, d, gscale,
-                                    l.ws, kWorkspaceBytes, l.stream);
+                                    nullptr, 0, l.ws, kWorkspaceBytes, l.stream);
     if (rc != IA_OK) return rc;
     IA_CUDA_CHECK(cudaMemcpyAsync(&partial[(size_t)ci], lslot, sizeof(float), cudaMemcpyDeviceToHost, l.stream));
     if (dx) {

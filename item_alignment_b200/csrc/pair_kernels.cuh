@@ -44,6 +44,9 @@ struct PairParams {
   double loss_scale;           // 1/n for mean, 1 otherwise
   void* workspace;
   int load_mode;               // bit 1: ld.global.cs instead of the no-allocate loads (0 in production; see the load loop)
+  int64_t rows_x, rows_y;      // gather: rows of the embedding matrices; an index outside [0, rows) poisons that pair with NaN
+  const float* upstream;       // fused: optional DEVICE scalar d(total)/d(loss) folded into the gradients (autograd backward)
+  int upstream_skip_one;       // with upstream: leave at once when *upstream == 1 (the gradients already in dx, dy are exact)
 };
 
 // Per-pair sums gathered in one sweep over the registers.
@@ -123,6 +126,14 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int nvec = p.d / E;
   float loss_acc = 0.f;
+  float gscale = p.grad_scale;
+  if (MODE == kModeFused && p.upstream != nullptr) {
+    // gradient recomputation of the autograd backward: the upstream scalar (GradScaler's 65536, 1/accum_steps, ...) is folded
+    // in BEFORE the one rounding to the gradient type, like the reference's fp32 backward does (finetune_text.py:479-482)
+    const float u = __ldg(p.upstream);
+    if (p.upstream_skip_one && u == 1.0f) return;
+    gscale *= u;
+  }
 
   extern __shared__ __align__(128) uint8_t ring_raw[];
   const uint32_t row_bytes = (uint32_t)p.d * (uint32_t)sizeof(T);
@@ -131,7 +142,7 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
   const int64_t row0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
   auto arm = [&](int stage, int64_t row) {   // lane 0 only
     uint8_t* dst = ring + (size_t)stage * 2 * row_bytes;
-    const int64_t rx = p.xi ? __ldg(p.xi + row) : row, ry = p.yi ? __ldg(p.yi + row) : row;
+    const int64_t rx = row, ry = row;   // the bulk ring is never used for gathered rows (launch_pair_vpl)
     mbar_arrive_expect_tx(&bars[stage], 2 * row_bytes);
     bulk_load_1d(dst, static_cast<const T*>(p.x) + rx * p.ldx, row_bytes, &bars[stage]);
     bulk_load_1d(dst + row_bytes, static_cast<const T*>(p.y) + ry * p.ldy, row_bytes, &bars[stage]);
@@ -151,12 +162,13 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
   const int64_t n_super = (p.n + ROWS - 1) / ROWS;
   for (int64_t rbase = row0; rbase < n_super; rbase += warps_total, ++it) {
     uint4 xv[ROWS][VPL], yv[ROWS][VPL];
-    bool live[ROWS];
+    bool live[ROWS], bad[ROWS];
     int64_t rows[ROWS];
 #pragma unroll
     for (int k = 0; k < ROWS; ++k) {
       rows[k] = rbase * ROWS + k;
       live[k] = rows[k] < p.n;
+      bad[k] = false;
     }
     if (BULK) {
       const int stage = it % kBulkStages;
@@ -177,8 +189,15 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
     } else {
 #pragma unroll
       for (int k = 0; k < ROWS; ++k) {
-        const int64_t rx = (p.xi && live[k]) ? __ldg(p.xi + rows[k]) : rows[k];
-        const int64_t ry = (p.yi && live[k]) ? __ldg(p.yi + rows[k]) : rows[k];
+        int64_t rx = rows[k], ry = rows[k];
+        if (p.xi != nullptr && live[k]) {
+          // gathered pair: an index outside the matrix reads row 0 instead and the pair's results become NaN (memory-safe;
+          // torch indexing in the reference loop, graph.py:87-117, would raise)
+          rx = __ldg(p.xi + rows[k]);
+          ry = __ldg(p.yi + rows[k]);
+          if ((uint64_t)rx >= (uint64_t)p.rows_x) { rx = 0; bad[k] = true; }
+          if ((uint64_t)ry >= (uint64_t)p.rows_y) { ry = 0; bad[k] = true; }
+        }
         const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.x) + rx * p.ldx);
         const uint4* yr = reinterpret_cast<const uint4*>(static_cast<const T*>(p.y) + ry * p.ldy);
 #pragma unroll
@@ -239,7 +258,8 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
       if (!live[k]) continue;
       const int64_t row = rows[k];
       float nx = 1.f, ny = 1.f;
-      const float sim = score_from_sums<MEASURE>(s[k], nx, ny);
+      float sim = score_from_sums<MEASURE>(s[k], nx, ny);
+      if (bad[k]) { sim = __int_as_float(0x7fc00000); s[k].xy = sim; }
 
       if (MODE != kModeBwd && lane == 0) {
         if (p.sim) p.sim[row] = sim;
@@ -260,11 +280,11 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
           float gc;
           if (label[k]) { li = 1.f - cs; gc = -1.f; }
           else { li = fmaxf(0.f, cs - p.margin); gc = (cs - p.margin) > 0.f ? 1.f : 0.f; }
-          gc *= p.grad_scale;
+          gc *= gscale;
           c.A = gc / den; c.Bx = gc * cs / a; c.By = gc * cs / b;
         } else {
           li = scalar_loss(p.loss, sim, label[k], p.margin, g);
-          c = score_grad_coef<MEASURE>(s[k], sim, nx, ny, g * p.grad_scale);
+          c = score_grad_coef<MEASURE>(s[k], sim, nx, ny, g * gscale);
         }
         if (p.reduction == IA_RED_NONE) { if (lane == 0) p.loss_out[row] = li; }
         else loss_acc += li;
@@ -327,9 +347,23 @@ __global__ void __launch_bounds__(256) pair_kernel_generic(const PairParams p) {
   const int warp_in_block = threadIdx.x >> 5;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   float loss_acc = 0.f;
+  float gscale = p.grad_scale;
+  if (MODE == kModeFused && p.upstream != nullptr) {
+    const float u = __ldg(p.upstream);
+    if (p.upstream_skip_one && u == 1.0f) return;
+    gscale *= u;
+  }
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_in_block; row < p.n; row += warps_total) {
-    const T* xr = static_cast<const T*>(p.x) + (p.xi ? __ldg(p.xi + row) : row) * p.ldx;
-    const T* yr = static_cast<const T*>(p.y) + (p.yi ? __ldg(p.yi + row) : row) * p.ldy;
+    int64_t rx = row, ry = row;
+    bool bad = false;
+    if (p.xi != nullptr) {
+      rx = __ldg(p.xi + row);
+      ry = __ldg(p.yi + row);
+      if ((uint64_t)rx >= (uint64_t)p.rows_x) { rx = 0; bad = true; }
+      if ((uint64_t)ry >= (uint64_t)p.rows_y) { ry = 0; bad = true; }
+    }
+    const T* xr = static_cast<const T*>(p.x) + rx * p.ldx;
+    const T* yr = static_cast<const T*>(p.y) + ry * p.ldy;
     RowSums s{0.f, 0.f, 0.f, 0.f};
     for (int j = lane; j < p.d; j += 32) {
       const float fx = to_float<T>(xr[j]), fy = to_float<T>(yr[j]);
@@ -337,7 +371,8 @@ __global__ void __launch_bounds__(256) pair_kernel_generic(const PairParams p) {
     }
     s.xy = warp_sum(s.xy); s.xx = warp_sum(s.xx); s.yy = warp_sum(s.yy); s.dist = warp_sum(s.dist);
     float nx = 1.f, ny = 1.f;
-    const float sim = score_from_sums<MEASURE>(s, nx, ny);
+    float sim = score_from_sums<MEASURE>(s, nx, ny);
+    if (bad) { sim = __int_as_float(0x7fc00000); s.xy = sim; }
     if (MODE != kModeBwd && lane == 0) {
       if (p.sim) p.sim[row] = sim;
       const float pr = prob_of<MEASURE>(sim);
@@ -356,11 +391,11 @@ __global__ void __launch_bounds__(256) pair_kernel_generic(const PairParams p) {
         float gc;
         if (label) { li = 1.f - cs; gc = -1.f; }
         else { li = fmaxf(0.f, cs - p.margin); gc = (cs - p.margin) > 0.f ? 1.f : 0.f; }
-        gc *= p.grad_scale;
+        gc *= gscale;
         c.A = gc / den; c.Bx = gc * cs / a; c.By = gc * cs / b;
       } else {
         li = scalar_loss(p.loss, sim, label, p.margin, g);
-        c = score_grad_coef<MEASURE>(s, sim, nx, ny, g * p.grad_scale);
+        c = score_grad_coef<MEASURE>(s, sim, nx, ny, g * gscale);
       }
       if (p.reduction == IA_RED_NONE) { if (lane == 0) p.loss_out[row] = li; }
       else loss_acc += li;
@@ -404,7 +439,8 @@ __global__ void __launch_bounds__(256) pair_kernel_generic(const PairParams p) {
 template <void (*kernel)(const PairParams)>
 int launch_rows(const PairParams& p, cudaStream_t stream) {
   constexpr int kThreads = 256, kWarps = 8;
-  static int cached_bps = 0;   // one instantiation per kernel -> per-kernel occupancy cache
+  static int cached_bps_dev[kMaxDevices] = {};   // one instantiation per kernel -> per-kernel, per-device occupancy cache
+  int& cached_bps = cached_bps_dev[device_slot()];
   if (cached_bps == 0) cached_bps = blocks_per_sm(kernel, kThreads);
   int64_t want = (p.n + kWarps - 1) / kWarps;
   int64_t cap = (int64_t)sm_count() * cached_bps;
@@ -422,8 +458,9 @@ int launch_rows_bulk(const PairParams& p, size_t elem_size, cudaStream_t stream)
   constexpr int kThreads = 256, kWarps = 8;
   const size_t smem = (size_t)kWarps * kBulkStages * 2 * (size_t)p.d * elem_size + kWarps * kBulkStages * 8;
   static size_t configured_dev[kMaxDevices] = {};   // function attributes are per context: one slot per device
-  static int cached_bps = 0;
+  static int cached_bps_dev[kMaxDevices] = {};
   size_t& configured = configured_dev[device_slot()];
+  int& cached_bps = cached_bps_dev[device_slot()];
   if (smem > configured) {
     IA_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
@@ -465,7 +502,7 @@ int launch_pair_vpl(const PairParams& p, bool vec_ok, cudaStream_t stream) {
   const int nvec = p.d / E;
   if (!vec_ok || nvec > 32 * 8) return launch_rows<pair_kernel_generic<T, G, MEASURE, MODE, COSLOSS>>(p, stream);
   // big rows (>= 1 KB) of the forward / fused kernels go through the bulk-copy ring
-  if (MODE != kModeBwd && pair_bulk_enabled() && (size_t)p.d * sizeof(T) >= 1024 && p.n >= 1024) {
+  if (MODE != kModeBwd && pair_bulk_enabled() && (size_t)p.d * sizeof(T) >= 1024 && p.n >= 1024 && p.xi == nullptr) {
     if (nvec <= 64) return launch_rows_bulk<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2, true, 1>>(p, sizeof(T), stream);
     if (nvec <= 128) return launch_rows_bulk<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, true, 1>>(p, sizeof(T), stream);
     return launch_rows_bulk<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8, true, 1>>(p, sizeof(T), stream);

@@ -37,6 +37,8 @@ struct HeadParams {
   int stages;         // ring depth (TRAIN)
   int group;          // adjacent pairs per ring stage (TRAIN): 2 for rows <= 3 KB, else 1
   int load_mode;      // bit 1: ld.global.cs (never set in production; pins the load order of the forward kernel)
+  const float* upstream;   // optional DEVICE scalar d(total)/d(loss) folded into every gradient (autograd backward)
+  int upstream_skip_one;   // with upstream: leave at once when *upstream == 1 (the gradients already written are exact)
 };
 
 constexpr int kHeadMaxGrid = 592;  // 148 SMs x 4
@@ -72,6 +74,12 @@ __global__ void __launch_bounds__(NW * 32, TRAIN ? 1 : 2) softmax_head_kernel(co
   constexpr int C = E / 4;            // float4 chunks per 128-bit input vector
   constexpr int P4 = VPL * 32 * C;    // float4 per (padded) weight-row half
   extern __shared__ float4 smem4[];
+  float gscale = p.grad_scale;
+  if (TRAIN && p.upstream != nullptr) {   // gradient recomputation with the upstream scalar folded in before the one rounding
+    const float u = __ldg(p.upstream);
+    if (p.upstream_skip_one && u == 1.0f) return;
+    gscale *= u;
+  }
   // [w0x | w0y | w1x | w1y | (TRAIN) wdx | wdy | sacc[2h] | ring]
   const float4* w0x = smem4;
   const float4* w0y = smem4 + P4;
@@ -257,7 +265,8 @@ __global__ void __launch_bounds__(NW * 32, TRAIN ? 1 : 2) softmax_head_kernel(co
         }
         if (TRAIN) {
           loss_acc += logf(den) - ((label[k] != 0 ? z1 : z0) - m);      // -log softmax[label]
-          delta[k] = (label[k] != 0 ? -p0 : p1) * p.grad_scale;          // d loss / d logit1 ( = -d loss / d logit0 )
+          if ((unsigned long long)label[k] > 1ull) loss_acc = __int_as_float(0x7fc00000);   // label outside {0,1}: the loss is NaN, loudly
+          delta[k] = (label[k] != 0 ? -p0 : p1) * gscale;          // d loss / d logit1 ( = -d loss / d logit0 )
           db_acc += delta[k];
         }
       }
@@ -361,7 +370,8 @@ __global__ void __launch_bounds__(NW * 32, TRAIN ? 1 : 2) softmax_head_kernel(co
 // dW[1][j] = sum over blocks of partial[b][j] (fixed order: lane-strided partial sums, then a shuffle tree);
 // dW[0] = -dW[1]; same for db.  One warp per column.
 __global__ void __launch_bounds__(256) softmax_head_finalize(const float* partials, int nblocks, int h2, float* dw,
-                                                             float* db) {
+                                                             float* db, const float* upstream, int skip_one) {
+  if (upstream != nullptr && skip_one && __ldg(upstream) == 1.0f) return;   // the main kernel left at once: no new partials
   const int lane = threadIdx.x & 31;
   const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (j > h2) return;
@@ -401,7 +411,7 @@ static int launch_head_rr(const HeadParams& p_in, int stages, size_t smem, cudaS
   if (TRAIN && (dw || db)) {
     const float* partials = reinterpret_cast<const float*>(static_cast<const char*>(p.workspace) + kWorkspaceBytes);
     const int h2 = 2 * p.h;
-    softmax_head_finalize<<<(h2 + 1 + 7) / 8, 256, 0, stream>>>(partials, grid, h2, dw, db);
+    softmax_head_finalize<<<(h2 + 1 + 7) / 8, 256, 0, stream>>>(partials, grid, h2, dw, db, p.upstream, p.upstream_skip_one);
     IA_LAUNCH_CHECK();
   }
   return IA_OK;
@@ -481,20 +491,22 @@ size_t ia_softmax_head_workspace_bytes(int64_t h) {
 int ia_softmax_head_fwd_bwd(int dtype, int grad_dtype, const void* x, const void* y, int64_t ldx, int64_t ldy,
                             const float* w, const float* b, const int64_t* labels, int64_t n, int64_t h,
                             float* logits, float* probs, float* loss_out, void* dx, void* dy, int64_t lddx,
-                            int64_t lddy, float* dw, float* db, float grad_scale, void* workspace,
-                            size_t workspace_bytes, ia_stream_t stream) {
+                            int64_t lddy, float* dw, float* db, float grad_scale, const float* upstream_dev,
+                            int skip_if_one, void* workspace, size_t workspace_bytes, ia_stream_t stream) {
   if (n < 0 || h <= 0 || ldx < h || ldy < h || w == nullptr || b == nullptr || (n > 0 && (x == nullptr || y == nullptr))) {
     set_error("bad arguments");
     return IA_ERR_INVALID;
   }
   const bool train = labels != nullptr;
-  if (train && loss_out == nullptr) { set_error("loss_out must not be NULL when labels are given"); return IA_ERR_INVALID; }
+  if (train && loss_out == nullptr && upstream_dev == nullptr) { set_error("loss_out must not be NULL when labels are given"); return IA_ERR_INVALID; }
   if ((dx == nullptr) != (dy == nullptr)) { set_error("dx and dy must both be given or both be NULL"); return IA_ERR_INVALID; }
   if (grad_dtype != dtype && grad_dtype != IA_F32) { set_error("grad_dtype must equal dtype or be fp32"); return IA_ERR_UNSUPPORTED; }
   if (train && (workspace == nullptr || workspace_bytes < ia_softmax_head_workspace_bytes(h))) {
     set_error("workspace too small: need %zu bytes", ia_softmax_head_workspace_bytes(h));
     return IA_ERR_WORKSPACE;
   }
+  if (train && loss_out == nullptr)   // gradient recomputation: the loss value is not wanted, it lands in the workspace header
+    loss_out = reinterpret_cast<float*>(static_cast<char*>(workspace) + kWorkspaceScratchOffset);
   const int elems = dtype == IA_F32 ? 4 : 8;
   const size_t es = dtype == IA_F32 ? 4 : 2, gs = grad_dtype == IA_F32 ? 4 : 2;
   auto al = [](const void* ptr, int64_t ld, size_t e) { return reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && (ld * (int64_t)e) % 16 == 0; };
@@ -505,8 +517,8 @@ int ia_softmax_head_fwd_bwd(int dtype, int grad_dtype, const void* x, const void
   }
   if (n == 0) {
     if (train) {
-      const float v = __builtin_nanf("");
-      IA_CUDA_CHECK(cudaMemcpyAsync(loss_out, &v, sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+      static const float kNan = __builtin_nanf("");   // static storage: the async copy may outlive this frame
+      IA_CUDA_CHECK(cudaMemcpyAsync(loss_out, &kNan, sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
       if (dw) IA_CUDA_CHECK(cudaMemsetAsync(dw, 0, sizeof(float) * 4 * h, (cudaStream_t)stream));
       if (db) IA_CUDA_CHECK(cudaMemsetAsync(db, 0, sizeof(float) * 2, (cudaStream_t)stream));
     }
@@ -518,6 +530,7 @@ int ia_softmax_head_fwd_bwd(int dtype, int grad_dtype, const void* x, const void
   p.grad_scale = (float)((double)grad_scale / (double)n);
   p.loss_scale = 1.0 / (double)n;
   p.workspace = workspace;
+  p.upstream = upstream_dev; p.upstream_skip_one = skip_if_one;
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == IA_F32) return launch_head<float, float>(p, train, s, dw, db);
   if (dtype == IA_BF16 && grad_dtype == IA_BF16) return launch_head<__nv_bfloat16, __nv_bfloat16>(p, train, s, dw, db);

@@ -82,6 +82,16 @@ def pair_score_bwd_raw(measure, x, y, gsim, grad_dtype=None):
     return dx, dy
 
 
+def _labels_i64(labels, n):
+    labels = labels.view(-1)
+    if labels.dtype != torch.int64:
+        labels = labels.to(torch.int64)      # bce: float labels are accepted, {0,1} semantics (SURVEY 2a)
+    labels = labels.contiguous()
+    if labels.numel() != n:
+        raise ValueError("labels must have one entry per pair")
+    return labels
+
+
 def pair_score_loss_raw(measure, loss_type, x, y, labels, margin=1.0, reduction="mean", grad_dtype=None,
                         grad_scale=1.0, want_grads=True):
     """ONE kernel: sim, probs, loss, dx, dy (reference head + ladder + backward; see include/ia_b200.h)."""
@@ -89,12 +99,7 @@ def pair_score_loss_raw(measure, loss_type, x, y, labels, margin=1.0, reduction=
     n, d = x.shape
     if loss_type not in LOSSES:
         raise ValueError(f"unsupported loss_type for a vector-similarity head: {loss_type}")
-    labels = labels.view(-1)
-    if labels.dtype != torch.int64:
-        labels = labels.to(torch.int64)      # bce: float labels are accepted, {0,1} semantics (SURVEY 2a)
-    labels = labels.contiguous()
-    if labels.numel() != n:
-        raise ValueError("labels must have one entry per pair")
+    labels = _labels_i64(labels, n)
     gd = grad_dtype or x.dtype
     dev = x.device
     sim = torch.empty(n, dtype=torch.float32, device=dev)
@@ -108,8 +113,29 @@ def pair_score_loss_raw(measure, loss_type, x, y, labels, margin=1.0, reduction=
             _measure_id(measure), LOSSES[loss_type], float(margin), REDUCTIONS[reduction], _DT[x.dtype], _DT[gd],
             x.data_ptr(), y.data_ptr(), _ld(x), _ld(y), labels.data_ptr(), n, d, sim.data_ptr(), probs.data_ptr(),
             loss.data_ptr(), dx.data_ptr() if want_grads else None, dy.data_ptr() if want_grads else None, d, d,
-            float(grad_scale), ws.data_ptr(), ws.numel(), _stream()))
+            float(grad_scale), None, 0, ws.data_ptr(), ws.numel(), _stream()))
     return sim, probs, (loss if reduction == "none" else loss[0]), dx, dy
+
+
+def pair_score_loss_regrad_(measure, loss_type, x, y, labels, margin, reduction, upstream, dx=None, dy=None):
+    """Gradients of the fused step for an upstream scalar that lives on the DEVICE (what autograd hands to backward():
+    GradScaler's scale under --fp16, 1/accumulation_steps, ...).  The scalar is folded in before the single rounding to
+    the gradient dtype -- 16-bit gradients neither underflow nor round twice (reference finetune_text.py:479-482 runs this
+    backward in fp32 on the already scaled loss).  With dx, dy given (the buffers the forward launch filled for upstream
+    == 1) the launch is a device-side no-op when the scalar is 1: no host sync, no traffic.  Returns (dx, dy)."""
+    n, d = x.shape
+    have = dx is not None
+    if not have:
+        dx = torch.empty((n, d), dtype=x.dtype, device=x.device)
+        dy = torch.empty((n, d), dtype=x.dtype, device=x.device)
+    up = upstream.detach().to(torch.float32).reshape(1).contiguous()
+    with torch.cuda.device(x.device):
+        ws = workspace(x.device)
+        check(lib().ia_pair_score_loss_fwd_bwd(
+            _measure_id(measure), LOSSES[loss_type], float(margin), REDUCTIONS[reduction], _DT[x.dtype], _DT[dx.dtype],
+            x.data_ptr(), y.data_ptr(), _ld(x), _ld(y), labels.data_ptr(), n, d, None, None, None, dx.data_ptr(),
+            dy.data_ptr(), d, d, 1.0, up.data_ptr(), int(have), ws.data_ptr(), ws.numel(), _stream()))
+    return dx, dy
 
 
 def scale_inplace_(a, b, g):
@@ -135,8 +161,10 @@ def score_loss_raw(loss_type, sim, target, margin=1.0, reduction="mean", want_gr
     return (out if reduction == "none" else out[0]), g
 
 
-def softmax_head_raw(x, y, w, b, labels=None, grad_dtype=None, want_grads=True, grad_scale=1.0):
-    """TwoTowerClassificationHead (+ CrossEntropyLoss fwd/bwd when labels are given), reference base.py:103-117."""
+def softmax_head_raw(x, y, w, b, labels=None, grad_dtype=None, want_grads=True, grad_scale=1.0, upstream=None, grads=None):
+    """TwoTowerClassificationHead (+ CrossEntropyLoss fwd/bwd when labels are given), reference base.py:103-117.
+    upstream (device scalar) / grads (dx, dy, dw, db of an earlier launch): gradient recomputation of the autograd
+    backward, see pair_score_loss_regrad_."""
     x, y = _prep(x, y)
     n, h = x.shape
     dev = x.device
@@ -144,13 +172,30 @@ def softmax_head_raw(x, y, w, b, labels=None, grad_dtype=None, want_grads=True, 
     b = b.detach().to(torch.float32).contiguous()
     if w.shape != (2, 2 * h) or b.shape != (2,):
         raise NotImplementedError("the CUDA softmax head supports num_labels == 2")
-    logits = torch.empty((n, 2), dtype=torch.float32, device=dev)
-    probs = torch.empty((n, 2), dtype=torch.float32, device=dev)
     train = labels is not None
     gd = grad_dtype or x.dtype
     loss = dx = dy = dw = db = None
     ws_ptr, ws_n = None, 0
+    regrad = upstream is not None
+    up = upstream.detach().to(torch.float32).reshape(1).contiguous() if regrad else None
     with torch.cuda.device(dev):
+        if regrad:
+            if grads is not None:
+                dx, dy, dw, db = grads
+            else:
+                dx = torch.empty((n, h), dtype=gd, device=dev)
+                dy = torch.empty((n, h), dtype=gd, device=dev)
+                dw = torch.empty((2, 2 * h), dtype=torch.float32, device=dev)
+                db = torch.empty(2, dtype=torch.float32, device=dev)
+            labels = labels.view(-1).to(torch.int64).contiguous()
+            ws = workspace(dev, lib().ia_softmax_head_workspace_bytes(h))
+            check(lib().ia_softmax_head_fwd_bwd(
+                _DT[x.dtype], _DT[dx.dtype], x.data_ptr(), y.data_ptr(), _ld(x), _ld(y), w.data_ptr(), b.data_ptr(),
+                labels.data_ptr(), n, h, None, None, None, dx.data_ptr(), dy.data_ptr(), h, h, dw.data_ptr(), db.data_ptr(),
+                1.0, up.data_ptr(), int(grads is not None), ws.data_ptr(), ws.numel(), _stream()))
+            return None, None, None, dx, dy, dw, db
+        logits = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        probs = torch.empty((n, 2), dtype=torch.float32, device=dev)
         if train:
             labels = labels.view(-1).to(torch.int64).contiguous()
             loss = torch.empty(1, dtype=torch.float32, device=dev)
@@ -166,12 +211,12 @@ def softmax_head_raw(x, y, w, b, labels=None, grad_dtype=None, want_grads=True, 
             labels.data_ptr() if train else None, n, h, logits.data_ptr(), probs.data_ptr(),
             loss.data_ptr() if train else None, dx.data_ptr() if dx is not None else None,
             dy.data_ptr() if dy is not None else None, h, h, dw.data_ptr() if dw is not None else None,
-            db.data_ptr() if db is not None else None, float(grad_scale), ws_ptr, ws_n, _stream()))
+            db.data_ptr() if db is not None else None, float(grad_scale), None, 0, ws_ptr, ws_n, _stream()))
     return logits, probs, (loss[0] if train else None), dx, dy, dw, db
 
 
 # ------------------------------------------------------------------------------------------- gather-and-score
-def _prep_gather(emb_x, emb_y, src_idx, tgt_idx):
+def _prep_gather(emb_x, emb_y, src_idx, tgt_idx, check_indices=True):
     if not (emb_x.is_cuda and emb_y.is_cuda):
         raise RuntimeError("item_alignment_b200 runs on CUDA tensors only (no CPU fallback)")
     if emb_x.dim() != 2 or emb_y.dim() != 2 or emb_x.shape[1] != emb_y.shape[1] or emb_x.dtype != emb_y.dtype:
@@ -186,13 +231,20 @@ def _prep_gather(emb_x, emb_y, src_idx, tgt_idx):
     tgt_idx = tgt_idx.to(device=emb_x.device, dtype=torch.int64).contiguous().view(-1)
     if src_idx.numel() != tgt_idx.numel():
         raise ValueError("src_idx and tgt_idx must have the same length")
+    if check_indices and src_idx.numel() > 0:
+        # what torch indexing in the reference loop (graph.py:87-117) would raise; one small reduction + one host read.
+        # (The kernels are memory-safe without it: an out-of-range index poisons that pair with NaN.)
+        bad = ((src_idx < 0) | (src_idx >= emb_x.shape[0]) | (tgt_idx < 0) | (tgt_idx >= emb_y.shape[0])).any()
+        if bool(bad):
+            raise IndexError(f"pair index out of range for embedding matrices with {emb_x.shape[0]} / {emb_y.shape[0]} rows")
     return emb_x, emb_y, src_idx, tgt_idx
 
 
-def pair_score_gather_raw(measure, emb_x, emb_y, src_idx, tgt_idx, threshold=None):
+def pair_score_gather_raw(measure, emb_x, emb_y, src_idx, tgt_idx, threshold=None, check_indices=True):
     """Scores of pairs given as row indices into embedding matrices, one launch (replaces the per-pair loop of
-    reference src/models/graph.py:87-117).  Returns sim, probs, labels-or-None.  Indices must be in range."""
-    emb_x, emb_y, src_idx, tgt_idx = _prep_gather(emb_x, emb_y, src_idx, tgt_idx)
+    reference src/models/graph.py:87-117).  Returns sim, probs, labels-or-None.  Out-of-range indices raise IndexError
+    (check_indices=False skips the host-side check: such pairs then come back as NaN)."""
+    emb_x, emb_y, src_idx, tgt_idx = _prep_gather(emb_x, emb_y, src_idx, tgt_idx, check_indices)
     n, d = src_idx.numel(), emb_x.shape[1]
     dev = emb_x.device
     sim = torch.empty(n, dtype=torch.float32, device=dev)
@@ -208,9 +260,9 @@ def pair_score_gather_raw(measure, emb_x, emb_y, src_idx, tgt_idx, threshold=Non
 
 
 def pair_score_loss_gather_raw(measure, loss_type, emb_x, emb_y, src_idx, tgt_idx, labels, margin=1.0, reduction="mean",
-                               grad_dtype=None, want_grads=True):
+                               grad_dtype=None, want_grads=True, check_indices=True):
     """Fused gather + score + loss + backward; dx, dy are dense per pair ([n, D])."""
-    emb_x, emb_y, src_idx, tgt_idx = _prep_gather(emb_x, emb_y, src_idx, tgt_idx)
+    emb_x, emb_y, src_idx, tgt_idx = _prep_gather(emb_x, emb_y, src_idx, tgt_idx, check_indices)
     n, d = src_idx.numel(), emb_x.shape[1]
     dev = emb_x.device
     if loss_type not in LOSSES:
@@ -226,8 +278,8 @@ def pair_score_loss_gather_raw(measure, loss_type, emb_x, emb_y, src_idx, tgt_id
         ws = workspace(dev)
         check(lib().ia_pair_score_gather_loss_fwd_bwd(
             _measure_id(measure), LOSSES[loss_type], float(margin), REDUCTIONS[reduction], _DT[emb_x.dtype], _DT[gd],
-            emb_x.data_ptr(), emb_y.data_ptr(), _ld(emb_x), _ld(emb_y), src_idx.data_ptr(), tgt_idx.data_ptr(),
-            labels.data_ptr(), n, d, sim.data_ptr(), probs.data_ptr(), loss.data_ptr(),
+            emb_x.data_ptr(), emb_y.data_ptr(), emb_x.shape[0], emb_y.shape[0], _ld(emb_x), _ld(emb_y), src_idx.data_ptr(),
+            tgt_idx.data_ptr(), labels.data_ptr(), n, d, sim.data_ptr(), probs.data_ptr(), loss.data_ptr(),
             dx.data_ptr() if want_grads else None, dy.data_ptr() if want_grads else None, d, d, 1.0, ws.data_ptr(),
             ws.numel(), _stream()))
     return sim, probs, loss[0], dx, dy
@@ -237,8 +289,10 @@ class _GatherPairLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, emb_x, emb_y, src_idx, tgt_idx, labels, measure, loss_type, margin, reduction):
         need = emb_x.requires_grad or emb_y.requires_grad
+        # per-pair gradients in fp32: they are scattered (index_add) in fp32 anyway, and the upstream scalar (GradScaler,
+        # 1/accum) is applied out of place to the fp32 sums before the one rounding to the embedding dtype
         sim, probs, loss, dx, dy = pair_score_loss_gather_raw(measure, loss_type, emb_x, emb_y, src_idx, tgt_idx, labels, margin,
-                                                              reduction, want_grads=need)
+                                                              reduction, grad_dtype=torch.float32, want_grads=need)
         if need:
             ctx.save_for_backward(dx, dy, src_idx, tgt_idx)
         ctx.shapes = (emb_x.shape, emb_y.shape, emb_x.dtype, emb_y.dtype)
@@ -248,10 +302,10 @@ class _GatherPairLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gloss, _gs, _gp):
         dx, dy, src_idx, tgt_idx = ctx.saved_tensors
-        scale_inplace_(dx, dy, gloss)
         sx, sy, tx, ty = ctx.shapes
-        gx = torch.zeros(sx, dtype=torch.float32, device=dx.device).index_add_(0, src_idx, dx.float()).to(tx)
-        gy = torch.zeros(sy, dtype=torch.float32, device=dy.device).index_add_(0, tgt_idx, dy.float()).to(ty)
+        g = gloss.detach().to(torch.float32)
+        gx = (torch.zeros(sx, dtype=torch.float32, device=dx.device).index_add_(0, src_idx, dx) * g).to(tx)
+        gy = (torch.zeros(sy, dtype=torch.float32, device=dy.device).index_add_(0, tgt_idx, dy) * g).to(ty)
         return gx, gy, None, None, None, None, None, None, None
 
 
@@ -366,23 +420,34 @@ class _PairScoreFn(torch.autograd.Function):
 
 
 class _FusedPairLossFn(torch.autograd.Function):
-    """(loss, sim, probs) from ONE kernel that also produced dx, dy; backward only rescales by the upstream
-    scalar (a device-side no-op when it is 1)."""
+    """(loss, sim, probs) from ONE kernel that also produced dx, dy for an upstream gradient of 1.
+
+    backward(): the common case (a plain loss.backward()) hands those buffers over untouched -- the gradient launch it
+    issues is a device-side no-op when the upstream scalar is 1, and there is no host sync.  Any other upstream scalar
+    (GradScaler under --fp16, loss / accumulation_steps) recomputes dx, dy from x, y with the scalar folded in BEFORE the
+    single rounding to the input dtype, which is what the reference's fp32 backward on the scaled loss does
+    (finetune_text.py:479-482); same traffic as rescaling the buffers would cost, but fp16 gradients of a mean over 64k
+    pairs do not flush to zero first.  The forward's buffers are handed out once; a second backward through the same node
+    (retain_graph=True) recomputes into fresh buffers, so nothing is ever scaled twice."""
 
     @staticmethod
     def forward(ctx, x, y, labels, measure, loss_type, margin, reduction):
         need = x.requires_grad or y.requires_grad
+        labels = _labels_i64(labels, x.shape[0])
         sim, probs, loss, dx, dy = pair_score_loss_raw(measure, loss_type, x, y, labels, margin, reduction, want_grads=need)
-        ctx.need = need
         if need:
-            ctx.save_for_backward(dx, dy)
+            ctx.save_for_backward(x, y, labels)
+            ctx.first = (dx, dy)
+            ctx.cfg = (measure, loss_type, margin, reduction)
         ctx.mark_non_differentiable(sim, probs)
         return loss, sim, probs
 
     @staticmethod
     def backward(ctx, gloss, _gsim, _gprobs):
-        dx, dy = ctx.saved_tensors
-        scale_inplace_(dx, dy, gloss)
+        x, y, labels = ctx.saved_tensors
+        first, ctx.first = ctx.first, None
+        dx, dy = first if first is not None else (None, None)
+        dx, dy = pair_score_loss_regrad_(*ctx.cfg[:2], x, y, labels, ctx.cfg[2], ctx.cfg[3], gloss, dx, dy)
         return dx, dy, None, None, None, None, None
 
 
@@ -426,20 +491,24 @@ class _SoftmaxHeadLogitsFn(torch.autograd.Function):
 
 
 class _FusedSoftmaxCEFn(torch.autograd.Function):
+    """Same contract as _FusedPairLossFn: the forward launch's gradients are handed out once, untouched when the upstream
+    scalar is 1 (device-side no-op); any other scalar, or a second backward, recomputes with the scalar folded in."""
+
     @staticmethod
     def forward(ctx, x, y, w, b, labels):
+        labels = labels.view(-1).to(torch.int64).contiguous()
         logits, probs, loss, dx, dy, dw, db = softmax_head_raw(x, y, w, b, labels)
-        ctx.save_for_backward(dx, dy, dw, db)
+        ctx.save_for_backward(x, y, w, b, labels)
+        ctx.first = (dx, dy, dw, db)
         ctx.wdtype, ctx.bdtype = w.dtype, b.dtype
         ctx.mark_non_differentiable(logits, probs)
         return loss, logits, probs
 
     @staticmethod
     def backward(ctx, gloss, _gl, _gp):
-        dx, dy, dw, db = ctx.saved_tensors
-        scale_inplace_(dx, dy, gloss)
-        scale_inplace_(dw, None, gloss)
-        scale_inplace_(db, None, gloss)
+        x, y, w, b, labels = ctx.saved_tensors
+        first, ctx.first = ctx.first, None
+        _, _, _, dx, dy, dw, db = softmax_head_raw(x, y, w, b, labels, upstream=gloss, grads=first)
         return dx, dy, dw.to(ctx.wdtype), db.to(ctx.bdtype), None
 
 

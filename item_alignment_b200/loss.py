@@ -69,7 +69,12 @@ def two_tower_step(classifier, config, features_1, features_2, labels=None):
     from .heads import TwoTowerClassificationHead, VecSimClassificationHead
     loss = None
     if isinstance(classifier, VecSimClassificationHead):
-        if labels is not None and config.loss_type in ("cosine", "bce", "hinge", "euclidean"):
+        if labels is not None:
+            if config.loss_type not in ("cosine", "bce", "hinge", "euclidean"):
+                # the reference ladder (text.py:1468-1477) would hand the [N] similarity vector to CrossEntropyLoss and
+                # fail inside it; fail here, loudly, instead of returning loss=None
+                raise ValueError(f"loss_type {config.loss_type!r} is not defined for a vector-similarity head "
+                                 "(use cosine, bce, hinge or euclidean; 'ce' belongs to the softmax two-tower head)")
             x, y, logits, probs, loss = classifier.forward_with_loss(features_1, features_2, labels, config.loss_type,
                                                                      getattr(config, "loss_margin", 1.0))
         else:

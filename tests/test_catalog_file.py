@@ -64,6 +64,38 @@ def test_catalog_file_rejects_garbage(tmp_path):
         ia.CatalogFile(good)
 
 
+def test_catalog_file_rejects_crafted_headers(tmp_path):
+    """header fields come from the file -- sizes that wrap around 2^64 and id-offset tables that run backwards or
+    past the blob must be rejected at open, not crash a later read."""
+    import item_alignment_b200 as ia
+    good = tmp_path / "good.iacat"
+    ia.write_catalog(good, torch.arange(32, dtype=torch.float32).view(4, 8), ids=["a", "bb", "ccc", "dddd"])
+    raw0 = good.read_bytes()
+    with ia.CatalogFile(good) as f:
+        assert [f.id(i) for i in range(4)] == ["a", "bb", "ccc", "dddd"]
+    ids_offset = int.from_bytes(raw0[40:48], "little")
+
+    def reject(mutate):
+        raw = bytearray(raw0)
+        mutate(raw)
+        path = tmp_path / "crafted.iacat"
+        path.write_bytes(bytes(raw))
+        with pytest.raises(ValueError):
+            ia.CatalogFile(path)
+
+    # rows * dim * 4 wraps to a small number: 2^61 rows x 8 columns x 4 bytes == 0 (mod 2^64)
+    reject(lambda r: r.__setitem__(slice(16, 24), (1 << 61).to_bytes(8, "little")))
+    # dim huge, rows * dim wraps
+    reject(lambda r: r.__setitem__(slice(24, 32), ((1 << 62) + 2).to_bytes(8, "little")))
+    # data_offset + data_bytes wraps
+    reject(lambda r: r.__setitem__(slice(32, 40), ((1 << 64) - 16).to_bytes(8, "little")))
+    # ids_offset + ids_bytes wraps
+    reject(lambda r: r.__setitem__(slice(48, 56), ((1 << 64) - 8).to_bytes(8, "little")))
+    # id offsets not monotone: off[1] beyond off[2] (a read of id 0 would run past the blob, id 1 gets a negative length)
+    reject(lambda r: r.__setitem__(slice(ids_offset + 8, ids_offset + 16), (1 << 40).to_bytes(8, "little")))
+    reject(lambda r: r.__setitem__(slice(ids_offset + 16, ids_offset + 24), (0).to_bytes(8, "little")))
+
+
 def _write_reference_jsonl(path, n_pairs, dim, seed):
     rng = np.random.default_rng(seed)
     items = {f"{i:032x}": np.tanh(rng.standard_normal(dim)).astype(np.float32) * np.float32(10.0 ** rng.integers(-6, 3))

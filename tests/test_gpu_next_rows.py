@@ -86,3 +86,24 @@ def test_find_best_f1_and_threshold_vs_reference_loop():
             ours = ia.find_best_f1_and_threshold(scores.to(DEV), labels.to(DEV), high)
             ref = torch_port.find_best_f1_and_threshold(scores.tolist(), labels.tolist(), high)
             assert ours == tuple(float(v) for v in ref), (n, ties, high, ours, ref)
+
+
+def test_gather_rejects_out_of_range_indices():
+    """a negative or >= M item id must neither read out of bounds nor pass silently: the Python mirror raises
+    IndexError (what torch indexing in the reference loop does); straight through the C ABI the pair is poisoned with NaN."""
+    import item_alignment_b200.functional as F_
+    emb = torch.tanh(torch.randn(40, 64, device=DEV))
+    src = torch.tensor([0, 5, 39, 7], device=DEV)
+    tgt = torch.tensor([1, 40, 2, -1], device=DEV)          # 40 and -1 are out of range
+    labels = torch.tensor([1, 0, 1, 0], device=DEV)
+    with pytest.raises(IndexError):
+        F_.pair_score_gather_raw("cosine", emb, emb, src, tgt)
+    with pytest.raises(IndexError):
+        F_.pair_score_loss_gather("cosine", "bce", emb, emb, src, tgt, labels)
+    for m in MEASURES:
+        sim, probs, _ = F_.pair_score_gather_raw(m, emb, emb, src, tgt, check_indices=False)
+        assert torch.isnan(sim[[1, 3]]).all() and torch.isfinite(sim[[0, 2]]).all()
+        ref = F_.pair_score_raw(m, emb[src[[0, 2]]], emb[tgt[[0, 2]]])[0]
+        assert torch.equal(sim[[0, 2]], ref)
+        out = F_.pair_score_loss_gather_raw(m, "hinge", emb, emb, src, tgt, labels, check_indices=False)
+        assert torch.isnan(out[2]) and torch.isfinite(out[3][[0, 2]]).all()

@@ -377,3 +377,147 @@ def test_host_buffer_entry_points(F_):
         assert ia.compute(x[0].tolist(), y[0].tolist()) == float(sim[0])
     finally:
         ia.configure("passthrough")
+
+
+# ----------------------------------------------------------------------------------------------- round 2
+@pytest.mark.parametrize("dt,m,l", [(torch.bfloat16, "inner_product", "bce"),            # BASELINE config 2: ROWS=2 instantiation
+                                    (torch.float32, "l1", "hinge"), (torch.float32, "l1", "euclidean"),   # config 3: 4 KB rows
+                                    (torch.float32, "l2", "hinge"), (torch.float32, "l2", "euclidean"),
+                                    (torch.float32, "cosine", "bce"), (torch.bfloat16, "cosine", "cosine"),
+                                    (torch.float32, "cosine", "hinge")])
+def test_benchmarked_instantiations_vs_oracle_at_full_size(F_, dt, m, l):
+    """The kernels bench.py times -- n >= 16384 selects the adjacent-row (ROWS=2) form for 1.5-3 KB rows, D=1024 fp32 the
+    4 KB-row form -- compared DIRECTLY with the oracle (reference head + ladder + backward on the CPU) at the full
+    65 536 x 1024 of BASELINE configs 2 and 3, on bench.py's own input recipe.  Gradients in fp32 (tolerance) and in the
+    input dtype (must equal the fp32 gradients rounded once)."""
+    from oracle import torch_port
+    import bench
+    n, d = bench.N_PAIRS, bench.DIM
+    x, y, labels = bench.make_pairs(torch, torch.device(DEV), bench.SEED + 2000, dt)
+    xc, yc, lc = x.cpu(), y.cpu(), labels.cpu()
+    rs, rp, rl, rdx, rdy = torch_port.pair_score_loss_fwd_bwd(m, l, xc, yc, lc, 1.0)
+    sim, probs, loss, dx, dy = F_.pair_score_loss_raw(m, l, x, y, labels, 1.0, "mean", grad_dtype=torch.float32)
+    rtol = _rtol(dt)
+    xf, yf = xc.float(), yc.float()
+    parity.assert_scores_close(m, sim, rs, xf, yf, rtol, f"{m}/{l} sim")
+    parity.assert_probs_close(probs, rp, rtol, parity.score_atol(m, xf, yf, rtol))
+    parity.assert_loss_close(loss, rl, 10 * rtol, 10 * float(parity.score_atol(m, xf, yf, rtol).max()))
+    tx, ty = parity.grad_term_scale(m if l != "cosine" else "cosine", xf, yf)
+    parity.assert_grad_close(dx, rdx, tx, 1.0 / n, 10 * rtol, f"{m}/{l} dx")
+    parity.assert_grad_close(dy, rdy, ty, 1.0 / n, 10 * rtol, f"{m}/{l} dy")
+    if dt != torch.float32:       # the timed form: gradients in the input dtype
+        _, _, loss2, dxl, dyl = F_.pair_score_loss_raw(m, l, x, y, labels, 1.0, "mean")
+        assert torch.equal(loss2, loss) and torch.equal(dxl, dx.to(dt)) and torch.equal(dyl, dy.to(dt))
+    # the host-buffer entry point bench.py's e2e leg calls (chunked, three streams) returns the same gradients
+    if (dt, m, l) == (torch.bfloat16, "inner_product", "bce"):
+        from item_alignment_b200 import _lib
+        lib = _lib.lib()
+        xh, yh, lh = xc.pin_memory(), yc.pin_memory(), lc.pin_memory()
+        dxh, dyh = torch.empty_like(xh).pin_memory(), torch.empty_like(yh).pin_memory()
+        loss_h = torch.zeros(1)
+        _lib.check(lib.ia_pair_score_loss_host(0, 0, 1.0, 1, _lib.IA_BF16, xh.data_ptr(), yh.data_ptr(), lh.data_ptr(), n, d,
+                                               loss_h.data_ptr(), dxh.data_ptr(), dyh.data_ptr(), 0))
+        assert torch.equal(dxh, dxl.cpu()) and torch.equal(dyh, dyl.cpu())
+        parity.assert_loss_close(loss_h[0], rl, 1e-4, 1e-4)
+
+
+@pytest.mark.parametrize("dt,h", [(torch.bfloat16, 1024), (torch.bfloat16, 768), (torch.float16, 512), (torch.float32, 1024)])
+def test_softmax_head_ce_vs_oracle_at_full_size(F_, dt, h):
+    """The softmax head + CE training kernels at the benchmarked size (65 536 pairs) against the oracle."""
+    from oracle import torch_port
+    n = 65536
+    gen = torch.Generator().manual_seed(77 + h)
+    x = torch.tanh(torch.randn(n, h, generator=gen)).to(dt)
+    y = torch.tanh(torch.randn(n, h, generator=gen)).to(dt)
+    labels = (torch.rand(n, generator=gen) < 0.5).long()
+    w = torch.randn(2, 2 * h, generator=gen) * 0.05
+    b = torch.randn(2, generator=gen) * 0.1
+    rlog, rprob, rl, rdx, rdy, rdw, rdb = torch_port.softmax_head_ce_fwd_bwd(x, y, w, b, labels)
+    logits, probs, loss, dx, dy, dw, db = F_.softmax_head_raw(x.to(DEV), y.to(DEV), w.to(DEV), b.to(DEV), labels.to(DEV),
+                                                              grad_dtype=torch.float32)
+    rtol = _rtol(dt)
+    scale = float((x.float().norm(dim=1).max() + y.float().norm(dim=1).max()) * w.norm(dim=1).max())
+    np.testing.assert_allclose(logits.cpu().numpy(), rlog.numpy(), rtol=rtol, atol=rtol * scale)
+    np.testing.assert_allclose(probs.cpu().numpy(), rprob.numpy(), rtol=rtol, atol=rtol * scale)
+    np.testing.assert_allclose(float(loss), float(rl), rtol=10 * rtol)
+    wd = (w[1] - w[0]).abs().max().item()
+    np.testing.assert_allclose(dx.cpu().numpy(), rdx.numpy(), rtol=10 * rtol, atol=10 * rtol * wd / n)
+    np.testing.assert_allclose(dy.cpu().numpy(), rdy.numpy(), rtol=10 * rtol, atol=10 * rtol * wd / n)
+    # dW sums 65 536 terms of either sign in fp32 (block partials in a fixed order): bound by the sum of magnitudes
+    mag = float((x.float().abs().mean(0).max())) * 1.0
+    np.testing.assert_allclose(dw.cpu().numpy(), rdw.numpy(), rtol=1e-3, atol=2e-5 * mag)
+    np.testing.assert_allclose(db.cpu().numpy(), rdb.numpy(), rtol=1e-3, atol=2e-5)
+
+
+def test_autograd_upstream_scale_fp16_gradscaler_and_second_backward(F_):
+    """(a) under GradScaler (finetune_text.py:479-482 with --fp16) the upstream scalar must be applied before
+    the gradients are rounded to fp16 -- a mean over 64k pairs makes every unscaled fp16 gradient subnormal; (b) a second
+    backward through the same node (retain_graph) must not scale anything twice."""
+    from oracle import torch_port
+    n, d = 65536, 256
+    gen = torch.Generator().manual_seed(5)
+    x = torch.tanh(torch.randn(n, d, generator=gen)).to(torch.float16)
+    y = torch.tanh(torch.randn(n, d, generator=gen)).to(torch.float16)
+    labels = (torch.rand(n, generator=gen) < 0.5).long()
+    rs, rp, rl, rdx, rdy = torch_port.pair_score_loss_fwd_bwd("cosine", "bce", x, y, labels)
+    scale = 65536.0
+    for m, l in (("cosine", "bce"),):
+        xd, yd = x.to(DEV).requires_grad_(True), y.to(DEV).requires_grad_(True)
+        sim, probs, loss = F_.pair_score_loss(m, l, xd, yd, labels.to(DEV))
+        (loss * scale).backward(retain_graph=True)                # scaler.scale(loss).backward()
+        ref = (rdx * scale)
+        got = xd.grad.float().cpu()
+        assert float(got.abs().max()) > 0
+        # one rounding of the exactly scaled fp32 gradient: within half an fp16 ulp (2^-11 relative) + fp32 noise
+        err = (got - ref).abs()
+        bound = ref.abs() * 2.0 ** -10 + 1e-3 * ref.abs().max(dim=1, keepdim=True).values + 1e-7
+        assert bool((err <= bound).all()), f"worst {float((err / bound).max()):.3g}x bound"
+        assert float((got != 0).float().mean()) > 0.99            # nothing flushed to zero
+        g1 = xd.grad.clone()
+        (loss * scale).backward()                                 # second backward through the same node
+        assert torch.equal(xd.grad, (g1.float() * 2).to(torch.float16))
+    # plain backward: the forward launch's buffers are handed over untouched (bitwise the raw kernel's gradients)
+    xd, yd = x.to(DEV).requires_grad_(True), y.to(DEV).requires_grad_(True)
+    _, _, loss = F_.pair_score_loss("cosine", "bce", xd, yd, labels.to(DEV))
+    loss.backward()
+    raw = F_.pair_score_loss_raw("cosine", "bce", x.to(DEV), y.to(DEV), labels.to(DEV))
+    assert torch.equal(xd.grad, raw[3]) and torch.equal(yd.grad, raw[4])
+    # softmax head + CE: same contract
+    h = d
+    w = (torch.randn(2, 2 * h, generator=gen) * 0.05).to(DEV).requires_grad_(True)
+    b = torch.zeros(2, device=DEV, requires_grad=True)
+    xd, yd = x.to(DEV).requires_grad_(True), y.to(DEV).requires_grad_(True)
+    _, _, loss = F_.softmax_head_ce(xd, yd, w, b, labels.to(DEV))
+    (loss * scale).backward(retain_graph=True)
+    _, _, _, odx, ody, odw, odb = torch_port.softmax_head_ce_fwd_bwd(x, y, w.detach().cpu(), b.detach().cpu(), labels)
+    got = xd.grad.float().cpu()
+    ref = odx * scale
+    assert bool(((got - ref).abs() <= ref.abs() * 2.0 ** -10 + 1e-3 * ref.abs().max() + 1e-7).all())
+    np.testing.assert_allclose(w.grad.cpu().numpy(), (odw * scale).numpy(), rtol=1e-3, atol=1e-3 * float((odw * scale).abs().max()))
+    g1, w1 = xd.grad.clone(), w.grad.clone()
+    (loss * scale).backward()
+    assert torch.equal(xd.grad, (g1.float() * 2).to(torch.float16))
+    torch.testing.assert_close(w.grad, w1 * 2, rtol=1e-6, atol=0)
+
+
+def test_loss_ladder_rejects_unsupported_combinations():
+    """a VecSim head with loss_type 'ce' (or an unknown loss) must fail loudly, not return loss=None."""
+    import types
+    import item_alignment_b200 as ia
+    cfg = types.SimpleNamespace(cls_layers="12", cls_pool="cls", hidden_size=64, classifier_dropout=0.0,
+                                hidden_dropout_prob=0.0, similarity_measure="cosine", loss_type="ce", loss_margin=1.0)
+    head = ia.VecSimClassificationHead(cfg).to(DEV)
+    f = torch.randn(8, 64, device=DEV)
+    labels = torch.randint(0, 2, (8,), device=DEV)
+    with pytest.raises(ValueError, match="loss_type"):
+        ia.two_tower_step(head, cfg, f, f, labels)
+    cfg.loss_type = "focal"
+    with pytest.raises(ValueError, match="loss_type"):
+        ia.two_tower_step(head, cfg, f, f, labels)
+    out = ia.two_tower_step(head, cfg, f, f, None)      # no labels: no loss, like the reference
+    assert out["loss"] is None and out["probs"].shape == (8,)
+    # CE labels outside {0,1} (e.g. ignore_index = -100, which this head does not offer) poison the loss with NaN
+    tt = ia.TwoTowerClassificationHead(64).to(DEV)
+    bad = labels.clone(); bad[3] = -100
+    assert torch.isnan(ia.functional.softmax_head_ce(f, f, tt.out_proj.weight, tt.out_proj.bias, bad)[2])
+    assert torch.isfinite(ia.functional.softmax_head_ce(f, f, tt.out_proj.weight, tt.out_proj.bias, labels)[2])
