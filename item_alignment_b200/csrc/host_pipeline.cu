@@ -5,6 +5,7 @@
 // [H2D chunk -> kernel -> D2H results] on its own device staging buffers, so the PCIe upload of chunk
 // i+1 overlaps the kernel and the download of chunk i (PCIe is full duplex).  Pinned host memory gives
 // full link speed; pageable memory works but is staged by the driver.
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -82,7 +83,10 @@ struct DeviceScope {
 };
 
 static int64_t chunk_rows_for(int64_t n, int64_t row_bytes) {
-  int64_t rows = (16ll << 20) / (row_bytes > 0 ? row_bytes : 1);   // ~16 MiB of x per chunk
+  // bytes of x per chunk.  Small chunks shorten the pipeline's fill and drain (the first upload and the last download are
+  // not overlapped with anything); large chunks amortise the per-chunk API calls.  IA_HOST_CHUNK_MB overrides (A/B runs).
+  static const int64_t chunk_bytes = [] { const char* e = getenv("IA_HOST_CHUNK_MB"); const int v = e ? atoi(e) : 0; return (int64_t)(v > 0 ? v : 16) << 20; }();
+  int64_t rows = chunk_bytes / (row_bytes > 0 ? row_bytes : 1);
   if (rows < 1024) rows = 1024;
   if (rows > n) rows = n;
   return rows;

@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
           li = scalar_loss(p.loss, sim, label[k], p.margin, g);
           c = score_grad_coef<MEASURE>(s[k], sim, nx, ny, g * gscale);
         }
+        if (bad[k]) li = sim;   // NaN (fmaxf in the hinge / cosine-embedding losses would swallow it)
         if (p.reduction == IA_RED_NONE) { if (lane == 0) p.loss_out[row] = li; }
         else loss_acc += li;
       } else {
@@ -397,6 +398,7 @@ __global__ void __launch_bounds__(256) pair_kernel_generic(const PairParams p) {
         li = scalar_loss(p.loss, sim, label, p.margin, g);
         c = score_grad_coef<MEASURE>(s, sim, nx, ny, g * gscale);
       }
+      if (bad) li = sim;
       if (p.reduction == IA_RED_NONE) { if (lane == 0) p.loss_out[row] = li; }
       else loss_acc += li;
     } else {

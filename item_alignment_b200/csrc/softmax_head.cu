@@ -11,37 +11,10 @@
 // dlogit0 = -delta, so dW[0] = -dW[1] and db[0] = -db[1].
 #include <cstdlib>
 
-#include "common.cuh"
-#include "ptx_sm100.cuh"
+#include "softmax_head.cuh"
 
 namespace ia {
 
-struct HeadParams {
-  const void* x;
-  const void* y;
-  int64_t ldx, ldy;
-  const float* w;   // [2, 2h]
-  const float* b;   // [2]
-  const int64_t* labels;
-  int64_t n;
-  int h;
-  float* logits;    // [n,2] or null
-  float* probs;     // [n,2] or null
-  float* loss_out;  // scalar
-  void* dx;
-  void* dy;
-  int64_t lddx, lddy;
-  float grad_scale;   // upstream / n
-  double loss_scale;  // 1/n
-  void* workspace;    // [kWorkspaceBytes | float partial[grid][2h+2]]
-  int stages;         // ring depth (TRAIN)
-  int group;          // adjacent pairs per ring stage (TRAIN): 2 for rows <= 3 KB, else 1
-  int load_mode;      // bit 1: ld.global.cs (never set in production; pins the load order of the forward kernel)
-  const float* upstream;   // optional DEVICE scalar d(total)/d(loss) folded into every gradient (autograd backward)
-  int upstream_skip_one;   // with upstream: leave at once when *upstream == 1 (the gradients already written are exact)
-};
-
-constexpr int kHeadMaxGrid = 592;  // 148 SMs x 4
 
 // Shared-memory layout of one weight-row half (h floats): "lane-interleaved chunks" -- the float4 a lane needs for
 // input vector v = lane + 32*i, chunk q sits at float4 index (i*(E/4)+q)*32 + lane, so every LDS.128 of a warp
@@ -532,6 +505,9 @@ int ia_softmax_head_fwd_bwd(int dtype, int grad_dtype, const void* x, const void
   p.workspace = workspace;
   p.upstream = upstream_dev; p.upstream_skip_one = skip_if_one;
   cudaStream_t s = (cudaStream_t)stream;
+  // 16-bit rows, training: the tensor-core kernel (softmax_head_mma.cu); IA_HEAD_MMA=0 keeps the CUDA-core kernel (A/B runs)
+  static const int use_mma = [] { const char* e = getenv("IA_HEAD_MMA"); return e ? atoi(e) : 1; }();
+  if (use_mma && train && softmax_head_mma_eligible(dtype, p)) return launch_softmax_head_mma(dtype, grad_dtype, p, s, dw, db);
   if (dtype == IA_F32) return launch_head<float, float>(p, train, s, dw, db);
   if (dtype == IA_BF16 && grad_dtype == IA_BF16) return launch_head<__nv_bfloat16, __nv_bfloat16>(p, train, s, dw, db);
   if (dtype == IA_BF16) return launch_head<__nv_bfloat16, float>(p, train, s, dw, db);

@@ -161,7 +161,8 @@ def score_loss_raw(loss_type, sim, target, margin=1.0, reduction="mean", want_gr
     return (out if reduction == "none" else out[0]), g
 
 
-def softmax_head_raw(x, y, w, b, labels=None, grad_dtype=None, want_grads=True, grad_scale=1.0, upstream=None, grads=None):
+def softmax_head_raw(x, y, w, b, labels=None, grad_dtype=None, want_grads=True, grad_scale=1.0, upstream=None, grads=None,
+                     want_wgrads=True):
     """TwoTowerClassificationHead (+ CrossEntropyLoss fwd/bwd when labels are given), reference base.py:103-117.
     upstream (device scalar) / grads (dx, dy, dw, db of an earlier launch): gradient recomputation of the autograd
     backward, see pair_score_loss_regrad_."""
@@ -202,8 +203,9 @@ def softmax_head_raw(x, y, w, b, labels=None, grad_dtype=None, want_grads=True, 
             if want_grads:
                 dx = torch.empty((n, h), dtype=gd, device=dev)
                 dy = torch.empty((n, h), dtype=gd, device=dev)
-                dw = torch.empty((2, 2 * h), dtype=torch.float32, device=dev)
-                db = torch.empty(2, dtype=torch.float32, device=dev)
+                if want_wgrads:      # False: frozen head (dx, dy only; the dW / db finalize launch is skipped)
+                    dw = torch.empty((2, 2 * h), dtype=torch.float32, device=dev)
+                    db = torch.empty(2, dtype=torch.float32, device=dev)
             ws = workspace(dev, lib().ia_softmax_head_workspace_bytes(h))
             ws_ptr, ws_n = ws.data_ptr(), ws.numel()
         check(lib().ia_softmax_head_fwd_bwd(

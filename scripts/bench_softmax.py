@@ -32,7 +32,8 @@ for dt, h in ((torch.bfloat16, 1024), (torch.bfloat16, 768), (torch.float32, 102
     b = torch.zeros(2, device=dev)
     e = x.element_size()
     t_train = timed(lambda: F_.softmax_head_raw(x, y, w, b, l))
+    t_main = timed(lambda: F_.softmax_head_raw(x, y, w, b, l, want_wgrads=False))
     t_fwd = timed(lambda: F_.softmax_head_raw(x, y, w, b))
     by_train, by_fwd = n * (4 * h * e + 24), n * (2 * h * e + 16)
-    print(f"{str(dt):16s} h={h:5d}: train {t_train:7.1f} us ({by_train / t_train / 1e3:6.0f} GB/s, {by_train / t_train / 1e3 / 65.549:5.1f} %)   "
+    print(f"{str(dt):16s} h={h:5d}: train {t_train:7.1f} us ({by_train / t_train / 1e3:6.0f} GB/s, {by_train / t_train / 1e3 / 65.549:5.1f} %; without the dW finalize launch {t_main:6.1f} us)   "
           f"forward {t_fwd:6.1f} us ({by_fwd / t_fwd / 1e3:6.0f} GB/s, {by_fwd / t_fwd / 1e3 / 65.549:5.1f} %)", flush=True)
