@@ -39,7 +39,7 @@ typedef enum {
 typedef enum { IA_INNER = 0, IA_COSINE = 1, IA_L1 = 2, IA_L2 = 3 } ia_measure;
 /* config.loss_type on a VecSim head, src/models/text.py:1400-1409 ("ce" belongs to the softmax head) */
 typedef enum { IA_LOSS_BCE = 0, IA_LOSS_HINGE = 1, IA_LOSS_EUCLIDEAN = 2, IA_LOSS_COSINE = 3 } ia_loss;
-typedef enum { IA_F32 = 0, IA_BF16 = 1, IA_F16 = 2 } ia_dtype;
+typedef enum { IA_F32 = 0, IA_BF16 = 1, IA_F16 = 2, IA_F64 = 3 /* scores of ia_best_f1_threshold only */ } ia_dtype;
 /* _Loss.reduction, src/models/loss.py:58-68,122-134 */
 typedef enum { IA_RED_NONE = 0, IA_RED_MEAN = 1, IA_RED_SUM = 2 } ia_reduction;
 
@@ -116,6 +116,19 @@ int ia_pair_score_gather_loss_fwd_bwd(int measure, int loss, float margin, int r
 int ia_threshold_sweep(const float* probs, const int64_t* labels, int64_t n, const double* thresholds,
                        int nthr, uint64_t* counts, ia_stream_t stream);
 
+/* ---- best-F1 threshold search: reference finetune_bert.py:72-106 --------------------------------------
+ * Replaces the Python `sorted(zip(scores, labels), reverse=...)` + loop: a stable LSD radix sort of (score key, label) on
+ * the device (equal scores keep their input order, like Python's sort), a prefix count of the positives (label == 1), the F1
+ * of every cut point i in [0, n-2] in float64 with the loop's own operations, and the EARLIEST maximum (the loop's strict
+ * '>').  scores: fp32 (IA_F32) or fp64 (IA_F64); labels int64 {0,1}; n < 2^31.
+ * out5 (DEVICE, 5 doubles) = best accuracy, F1, precision, recall, threshold = mean of the scores on both sides of the cut;
+ * all zero when n < 2 or no cut has F1 > 0, as the reference returns.  workspace: ia_best_f1_workspace_bytes(n, score_dtype)
+ * bytes of device scratch, 256-byte aligned, no initialisation. */
+size_t ia_best_f1_workspace_bytes(int64_t n, int score_dtype);
+int ia_best_f1_threshold(int score_dtype, const void* scores, const int64_t* labels, int64_t n,
+                         int high_score_more_similar, double* out5, void* workspace, size_t workspace_bytes,
+                         ia_stream_t stream);
+
 /* ---- elementwise losses on a score vector (the reference's loss modules on their own) ---------
  * HingeLoss.forward (loss.py:126-134), EuclideanDistanceLoss.forward (loss.py:61-68), BCEWithLogits
  * (text.py:1403).  target_pm1: int64 in {-1,+1} for hinge / euclidean, {0,1} for bce.
@@ -140,6 +153,11 @@ int ia_softmax_head_fwd_bwd(int dtype, int grad_dtype, const void* x, const void
                             void* dx, void* dy, int64_t lddx, int64_t lddy, float* dw, float* db,
                             float grad_scale, const float* upstream_dev, int skip_if_one, void* workspace,
                             size_t workspace_bytes, ia_stream_t stream);
+
+/* Diagnostics: cycle counters of the last tensor-core softmax-head launch made with IA_HEAD_DEBUG=16 in the environment (summed
+ * over CTAs and warps): [0] forward warps waiting for rows, [1] at their barrier, [2] loader warps waiting for a released stage,
+ * [3] forward warps total, [4] backward warps waiting for deltas, [5] backward warps total, [6] warp 0's softmax section. */
+int ia_softmax_head_last_stats(uint64_t* out8);
 
 /* ---- in-place scale of gradients by a device scalar (autograd upstream != 1, e.g. GradScaler) --
  * No-op on the device when *g == 1.0f. */
@@ -200,6 +218,13 @@ int ia_catalog_topk(ia_catalog* cat, int measure, const void* queries, int64_t q
  * learnt in a cheap probe pass (ShardedCatalogIndex: min over ranks of each rank's ceil(k/G)-th best). */
 int ia_catalog_topk_seeded(ia_catalog* cat, int measure, const void* queries, int64_t q, int64_t ldq,
                            int k, const int64_t* tau_init, uint64_t* keys_out, ia_stream_t stream);
+/* Probe pass of a row shard (ShardedCatalogIndex): `groups` disjoint row groups of rows_per_group rows (a multiple of 256) at the
+ * head of the catalog are scanned with a top-kp each (kp <= 16: the kernel's register top-k path, no threshold sharing between
+ * groups); bound_out[q] (int64, DEVICE) = the smallest of the groups' kp-th best key words, 0 = no bound.  The ranks take the
+ * MIN over all ranks (one small all-reduce): (ranks * groups * kp) >= k rows meet that key, so it is a valid tau_init for
+ * ia_catalog_topk_seeded on every shard.  ia_catalog_topk runs the same probe on its own for k > 16 (IA_RETR_PROBE=0: off). */
+int ia_catalog_probe_bound(ia_catalog* cat, int measure, const void* queries, int64_t q, int64_t ldq, int kp,
+                           int groups, int64_t rows_per_group, int64_t* bound_out, ia_stream_t stream);
 /* Telemetry of the last ia_catalog_topk on this handle (synchronises the device): out8[0] keys appended to the
  * per-query buffers, [1] buffer->list merges, [2] 32-column groups that left the fast path, [3] rare-path
  * iterations, and epilogue-warp cycle sums: [4] waiting for accumulators, [5] in merges, [6] total, [7] rare path. */

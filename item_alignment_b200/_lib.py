@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("IA_B200_LIB", LIB_PATH)      # A/B builds of the same
 MEASURES = {"inner_product": 0, "cosine": 1, "l1": 2, "l2": 3}
 LOSSES = {"bce": 0, "hinge": 1, "euclidean": 2, "cosine": 3}
 REDUCTIONS = {"none": 0, "mean": 1, "sum": 2}
-IA_F32, IA_BF16, IA_F16 = 0, 1, 2
+IA_F32, IA_BF16, IA_F16, IA_F64 = 0, 1, 2, 3
 IA_MAX_K = 128
 
 _lib = None
@@ -39,12 +39,15 @@ SIGNATURES = {
                                                   c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                                   c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_size_t, c_void_p]),
     "ia_threshold_sweep": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
+    "ia_best_f1_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "ia_best_f1_threshold": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ia_score_loss_fwd_bwd": (c_int, [c_int, c_float, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_float,
                                       c_void_p, c_size_t, c_void_p]),
     "ia_softmax_head_workspace_bytes": (c_size_t, [c_int64]),
     "ia_softmax_head_fwd_bwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                         c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                         c_int64, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "ia_softmax_head_last_stats": (c_int, [c_void_p]),
     "ia_scale_inplace": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "ia_project_tanh_fwd": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p,
                                     c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
@@ -58,6 +61,7 @@ SIGNATURES = {
     "ia_catalog_destroy": (None, [c_void_p]),
     "ia_catalog_topk": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "ia_catalog_topk_seeded": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "ia_catalog_probe_bound": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p]),
     "ia_catalog_last_stats": (c_int, [c_void_p, c_void_p]),
     "ia_catalog_last_plan": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ia_catalog_topk_dissimilarity": (c_int, [c_void_p, c_int, c_float, c_int, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),

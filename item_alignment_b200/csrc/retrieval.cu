@@ -42,7 +42,9 @@ struct RetrParams {
   int dist_squared;     // l2: rank and report the squared distance (torchkge l2_dissimilarity)
   uint32_t row_base;    // global row id of catalog row 0 (shard offset)
   int flags;            // tuning switches for in-run A/B measurements (env IA_RETR_FLAGS, default 14): bit1 early tau
-                        // load, bit2 finished-split bound, bit3 paced merges (<= 2 lanes per tile after release)
+                        // load, bit2 finished-split bound, bit3 paced merges (<= 2 lanes per tile after release);
+                        // bit5 (32, set by probe passes): items neither read nor publish thresholds of other items --
+                        // every (query tile, row group) finds ITS OWN exact top-k
 };
 
 // A valid lower bound on the final k-th best key of a query from the FINISHED splits of its query tile:
@@ -225,7 +227,7 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       __syncwarp();
       uint32_t* tau_warp = p.tau_global + qt * BM + e * 32;
       TopKThread st{0ull, 0};
-      if (p.flags & 4) st.thr_key = finished_splits_bound(p, qt, split, e, row_local, BM);
+      if ((p.flags & 36) == 4) st.thr_key = finished_splits_bound(p, qt, split, e, row_local, BM);
       uint64_t top[KREG > 0 ? KREG : 1];
 #pragma unroll
       for (int i = 0; i < (KREG > 0 ? KREG : 1); ++i) top[i] = 0ull;
@@ -236,13 +238,13 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const float* cs = cinv_s + acc * BN;
         // what other CTAs have published for this query: issue the (L2-latency) load now, consume it after the waits
         uint32_t tau_seen = 0;
-        if (p.flags & 2) tau_seen = *reinterpret_cast<volatile uint32_t*>(tau_warp + lane);
+        if ((p.flags & 34) == 2) tau_seen = *reinterpret_cast<volatile uint32_t*>(tau_warp + lane);
         const long long w0 = clock64();
         if (COSINE) mbar_wait(&cfull_bar[acc], acc_phase);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         cyc_wait += clock64() - w0;
-        if (!(p.flags & 2)) tau_seen = *reinterpret_cast<volatile uint32_t*>(tau_warp + lane);
+        if (!(p.flags & 34)) tau_seen = *reinterpret_cast<volatile uint32_t*>(tau_warp + lane);
         {
           const uint64_t gk = (uint64_t)tau_seen << 32;
           if (gk > st.thr_key) st.thr_key = gk;
@@ -349,7 +351,7 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         if (KREG > 0) {   // publish an improved k-th best for the other CTAs working on these queries (once per tile)
           const uint32_t w = (uint32_t)(st.thr_key >> 32);
           // (thr_key may also hold a bound learnt from others; re-publishing that is harmless: atomicMax)
-          if (w > tau_published && q_ok) { atomicMax(tau_warp + lane, w); tau_published = w; }
+          if (w > tau_published && q_ok && !(p.flags & 32)) { atomicMax(tau_warp + lane, w); tau_published = w; }
         }
       }
       __syncwarp();
@@ -623,6 +625,29 @@ __global__ void __launch_bounds__(256) unpack_keys_kernel(const uint64_t* __rest
   }
 }
 
+// Lower bound from a probe pass: `groups` disjoint row groups were scanned with top-kp each (lists in the internal layout);
+// bound[q] = the smallest of their kp-th best keys' upper words (0 = some group holds fewer than kp rows: no bound).
+// groups * kp >= k rows are >= that key, so nothing below it can be in the top-k of the whole catalog.
+__global__ void __launch_bounds__(256) probe_bound_kernel(const uint64_t* __restrict__ lists, int groups, int n_qt, int tile_rows, int kp,
+                                                          int64_t q_rows, uint32_t* __restrict__ bound_u32, int64_t* __restrict__ bound_i64) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < q_rows; q += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t b = 0xFFFFFFFFu;
+    for (int g = 0; g < groups; ++g) {
+      const uint64_t key = __ldg(lists + (((size_t)g * n_qt + (size_t)(q / tile_rows)) * tile_rows + (size_t)(q % tile_rows)) * kListCap + (kp - 1));
+      const uint32_t w = (uint32_t)(key >> 32);
+      b = w < b ? w : b;
+    }
+    if (bound_u32) bound_u32[q] = b;
+    if (bound_i64) bound_i64[q] = (int64_t)b;
+  }
+}
+
+// tau_global seeded from device-resident u32 words (the library's own probe)
+__global__ void __launch_bounds__(256) seed_tau_u32_kernel(const uint32_t* __restrict__ init, uint32_t* __restrict__ tau, int64_t q_rows, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    tau[i] = i < q_rows ? init[i] : 0u;
+}
+
 // tau_global seeded from caller-provided lower bounds (goodness words held in int64), 0 = no bound
 __global__ void __launch_bounds__(256) seed_tau_kernel(const int64_t* __restrict__ init, uint32_t* __restrict__ tau, int64_t q_rows,
                                                        int64_t n) {
@@ -692,6 +717,7 @@ struct ia_catalog {
   uint64_t* lists; size_t lists_bytes;
   uint32_t* tau; size_t tau_bytes;      // [tau | done flags]
   float* qinv; size_t qinv_bytes;
+  uint32_t* bound; size_t bound_bytes;  // [q] probe bound words of the last call
   unsigned long long* stats;            // [8]
   int last_splits, last_tiles_per_split;
 };
@@ -740,7 +766,7 @@ int ia_catalog_create(ia_catalog** out, int dtype, const void* catalog, int64_t 
   if (!cat) { set_error("out of host memory"); return IA_ERR_CUDA; }
   cat->dtype = dtype; cat->data = catalog; cat->c = c; cat->d = d; cat->ld = ld; cat->row_base = (uint32_t)row_base;
   cat->lists = nullptr; cat->lists_bytes = 0; cat->tau = nullptr; cat->tau_bytes = 0; cat->qinv = nullptr; cat->qinv_bytes = 0;
-  cat->cinv = nullptr; cat->tc_ok = false; cat->stats = nullptr;
+  cat->cinv = nullptr; cat->tc_ok = false; cat->stats = nullptr; cat->bound = nullptr; cat->bound_bytes = 0;
   cudaGetDevice(&cat->device);
   cudaStream_t s = (cudaStream_t)stream;
   // inverse norms padded with zeros to whole 256-row tiles: the kernel bulk-copies one tile's worth at a time
@@ -770,6 +796,7 @@ void ia_catalog_destroy(ia_catalog* cat) {
   if (cat->lists) cudaFree(cat->lists);
   if (cat->tau) cudaFree(cat->tau);
   if (cat->qinv) cudaFree(cat->qinv);
+  if (cat->bound) cudaFree(cat->bound);
   if (cat->stats) cudaFree(cat->stats);
   delete cat;
 }
@@ -777,6 +804,54 @@ void ia_catalog_destroy(ia_catalog* cat) {
 int ia_catalog_topk(ia_catalog* cat, int measure, const void* queries, int64_t q, int64_t ldq, int k,
                     uint64_t* keys_out, ia_stream_t stream) {
   return ia_catalog_topk_seeded(cat, measure, queries, q, ldq, k, nullptr, keys_out, stream);
+}
+
+// one launch of the tensor-core kernel for the decomposition in p
+static int launch_tc(ia_catalog* cat, int measure, bool kreg, const CUtensorMap& tmap_q, const RetrParams& p, int grid, cudaStream_t s) {
+  const int fmt_bf16 = cat->dtype == IA_BF16;
+  auto launch = [&](auto kernel) -> int {
+    IA_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(tmap_q, cat->tmap_c, p);
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+  };
+  if (kreg) {
+    if (measure == IA_COSINE) return fmt_bf16 ? launch(retrieve_tc_kernel<true, 1, 16>) : launch(retrieve_tc_kernel<true, 0, 16>);
+    return fmt_bf16 ? launch(retrieve_tc_kernel<false, 1, 16>) : launch(retrieve_tc_kernel<false, 0, 16>);
+  }
+  if (measure == IA_COSINE) return fmt_bf16 ? launch(retrieve_tc_kernel<true, 1, 0>) : launch(retrieve_tc_kernel<true, 0, 0>);
+  return fmt_bf16 ? launch(retrieve_tc_kernel<false, 1, 0>) : launch(retrieve_tc_kernel<false, 0, 0>);
+}
+
+static int grow_scratch(ia_catalog* cat, int64_t n_items, int n_qt, int BM) {
+  int rc;
+  const size_t lists_n = (size_t)n_items * BM * kListCap, ov_n = (size_t)n_items * BM * kBufSlots;
+  if ((rc = grow((void**)&cat->lists, &cat->lists_bytes, sizeof(uint64_t) * (lists_n + ov_n))) != IA_OK) return rc;
+  const size_t tau_n = (size_t)n_qt * BM, done_n = (size_t)n_items * 4;
+  return grow((void**)&cat->tau, &cat->tau_bytes, sizeof(uint32_t) * (tau_n + done_n));
+}
+
+// Probe pass (tensor-core path): `groups` disjoint row groups of `tiles_per_group` 256-row tiles at the head of the catalog are
+// scanned with the register top-k (kp <= 16), every group on its own (no threshold sharing); cat->bound[q] = the smallest of
+// the groups' kp-th best key words.  The caller guarantees groups * kp >= the k it will ask for.
+static int probe_pass(ia_catalog* cat, int measure, const CUtensorMap& tmap_q, RetrParams p, int groups, int tiles_per_group, int kp,
+                      int64_t q, int64_t* bound_i64, cudaStream_t s) {
+  int rc;
+  p.k = kp;
+  p.n_splits = groups; p.tiles_per_split = tiles_per_group; p.n_tiles = groups * tiles_per_group;
+  p.flags |= 32;
+  const int64_t n_items = (int64_t)p.n_qt * groups;
+  if ((rc = grow_scratch(cat, n_items, p.n_qt, tc::BM)) != IA_OK) return rc;
+  if ((rc = grow((void**)&cat->bound, &cat->bound_bytes, sizeof(uint32_t) * (size_t)q)) != IA_OK) return rc;
+  const size_t tau_n = (size_t)p.n_qt * tc::BM, done_n = (size_t)n_items * 4;
+  IA_CUDA_CHECK(cudaMemsetAsync(cat->tau, 0, sizeof(uint32_t) * (tau_n + done_n), s));
+  p.lists = cat->lists; p.overflow = nullptr; p.tau_global = cat->tau; p.done = cat->tau + tau_n; p.stats = nullptr;
+  const int sms = sm_count();
+  if ((rc = launch_tc(cat, measure, true, tmap_q, p, (int)(n_items < sms ? n_items : sms), s)) != IA_OK) return rc;
+  const int64_t want = (q + 255) / 256;
+  probe_bound_kernel<<<(int)(want < 4 * sms ? want : 4 * sms), 256, 0, s>>>(cat->lists, groups, p.n_qt, tc::BM, kp, q, cat->bound, bound_i64);
+  IA_LAUNCH_CHECK();
+  return IA_OK;
 }
 
 static int catalog_topk_impl(ia_catalog* cat, int measure, float dist_eps, int dist_squared, const void* queries, int64_t q,
@@ -802,53 +877,60 @@ static int catalog_topk_impl(ia_catalog* cat, int measure, float dist_eps, int d
   p.dist_eps = dist_eps; p.dist_squared = dist_squared;
   p.flags = 14;
   if (const char* f = getenv("IA_RETR_FLAGS")) p.flags = atoi(f);
-  const int sms = sm_count();
-  int ctas = sms;
-  if (!use_tc) ctas = sms * 2;
-  const bool use_kreg = use_tc && k <= 16;
-  // cold-start cost per item in tiles: small when the caller seeds the thresholds or the list lives in registers
-  double penalty = (use_tc ? 0.3 : 0.15) * k;
-  if (use_tc && (tau_init != nullptr || use_kreg)) penalty = 2.0 + 0.03 * k;
-  if (const char* f = getenv("IA_RETR_PENALTY")) penalty = atof(f) * k;
-  plan_splits(p.n_qt, p.n_tiles, ctas, use_tc ? 8 : 4, penalty, &p.n_splits, &p.tiles_per_split);
-  const int64_t n_items = (int64_t)p.n_qt * p.n_splits;
-
+  p.cinv = cat->cinv;
   int rc;
-  const size_t lists_n = (size_t)n_items * BM * kListCap, ov_n = (size_t)n_items * BM * kBufSlots;
-  if ((rc = grow((void**)&cat->lists, &cat->lists_bytes, sizeof(uint64_t) * (lists_n + ov_n))) != IA_OK) return rc;
-  const size_t tau_n = (size_t)p.n_qt * BM, done_n = (size_t)n_items * 4;
-  if ((rc = grow((void**)&cat->tau, &cat->tau_bytes, sizeof(uint32_t) * (tau_n + done_n))) != IA_OK) return rc;
-  IA_CUDA_CHECK(cudaMemsetAsync(cat->tau, 0, sizeof(uint32_t) * (tau_n + done_n), s));
-  if (tau_init != nullptr) {
-    seed_tau_kernel<<<(int)((tau_n + 255) / 256), 256, 0, s>>>(tau_init, cat->tau, q, (int64_t)tau_n);
-    IA_LAUNCH_CHECK();
-  }
-  IA_CUDA_CHECK(cudaMemsetAsync(cat->stats, 0, sizeof(unsigned long long) * 8, s));
-  cat->last_splits = p.n_splits; cat->last_tiles_per_split = p.tiles_per_split;
-  p.lists = cat->lists; p.overflow = cat->lists + lists_n; p.tau_global = cat->tau; p.done = cat->tau + tau_n; p.cinv = cat->cinv; p.stats = cat->stats;
   if (measure == IA_COSINE) {
     if ((rc = grow((void**)&cat->qinv, &cat->qinv_bytes, sizeof(float) * (size_t)q)) != IA_OK) return rc;
     if ((rc = ia_row_inv_norm(cat->dtype, queries, q, cat->d, ldq, kCosEps, cat->qinv, stream)) != IA_OK) return rc;
     p.qinv = cat->qinv;
   }
+  const int sms = sm_count();
+  int ctas = sms;
+  if (!use_tc) ctas = sms * 2;
+  const bool use_kreg = use_tc && k <= 16;
+
+  // Cold start of a k > 16 scan: every (query tile, split) fills its 128-key lists from nothing, ~k (1 + ln(rows / k)) insertions
+  // per query (C4: 1 975 appends and 105 list merges per query).  A probe over 1/32 of the catalog on the register top-k path
+  // (ceil(k/16) row groups, top-ceil(k/groups) each) costs ~3 % of the scan and hands every item a threshold that >= k rows meet,
+  // so the main pass only collects what can still matter.  Same result by construction of the bound.  IA_RETR_PROBE=0: off.
+  static const int probe_on = [] { const char* e = getenv("IA_RETR_PROBE"); return e ? atoi(e) : 1; }();
+  bool seeded_by_probe = false;
+  if (use_tc && !use_kreg && tau_init == nullptr && probe_on) {
+    const int groups = (k + 15) / 16;
+    const int kp = (k + groups - 1) / groups;
+    int tpg = p.n_tiles / 32 / groups;
+    if (tpg < 4) tpg = 4;
+    if ((int64_t)groups * tpg * 4 <= p.n_tiles && (int64_t)groups * tpg * BN <= cat->c) {
+      if ((rc = probe_pass(cat, measure, tmap_q, p, groups, tpg, kp, q, nullptr, s)) != IA_OK) return rc;
+      seeded_by_probe = true;
+    }
+  }
+
+  // cold-start cost per item in tiles: small when the thresholds are seeded or the list lives in registers
+  double penalty = (use_tc ? 0.3 : 0.15) * k;
+  if (use_tc && (tau_init != nullptr || use_kreg || seeded_by_probe)) penalty = 2.0 + 0.03 * k;
+  if (const char* f = getenv("IA_RETR_PENALTY")) penalty = atof(f) * k;
+  plan_splits(p.n_qt, p.n_tiles, ctas, use_tc ? 8 : 4, penalty, &p.n_splits, &p.tiles_per_split);
+  const int64_t n_items = (int64_t)p.n_qt * p.n_splits;
+
+  if ((rc = grow_scratch(cat, n_items, p.n_qt, BM)) != IA_OK) return rc;
+  const size_t lists_n = (size_t)n_items * BM * kListCap;
+  const size_t tau_n = (size_t)p.n_qt * BM, done_n = (size_t)n_items * 4;
+  IA_CUDA_CHECK(cudaMemsetAsync(cat->tau, 0, sizeof(uint32_t) * (tau_n + done_n), s));
+  if (tau_init != nullptr) {
+    seed_tau_kernel<<<(int)((tau_n + 255) / 256), 256, 0, s>>>(tau_init, cat->tau, q, (int64_t)tau_n);
+    IA_LAUNCH_CHECK();
+  } else if (seeded_by_probe) {
+    seed_tau_u32_kernel<<<(int)((tau_n + 255) / 256), 256, 0, s>>>(cat->bound, cat->tau, q, (int64_t)tau_n);
+    IA_LAUNCH_CHECK();
+  }
+  IA_CUDA_CHECK(cudaMemsetAsync(cat->stats, 0, sizeof(unsigned long long) * 8, s));
+  cat->last_splits = p.n_splits; cat->last_tiles_per_split = p.tiles_per_split;
+  p.lists = cat->lists; p.overflow = cat->lists + lists_n; p.tau_global = cat->tau; p.done = cat->tau + tau_n; p.stats = cat->stats;
   const int grid = (int)(n_items < ctas ? n_items : ctas);
 
   if (use_tc) {
-    const int fmt_bf16 = cat->dtype == IA_BF16;
-    auto launch = [&](auto kernel) -> int {
-      IA_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-      kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(tmap_q, cat->tmap_c, p);
-      IA_LAUNCH_CHECK();
-      return IA_OK;
-    };
-    if (use_kreg) {
-      if (measure == IA_COSINE) rc = fmt_bf16 ? launch(retrieve_tc_kernel<true, 1, 16>) : launch(retrieve_tc_kernel<true, 0, 16>);
-      else rc = fmt_bf16 ? launch(retrieve_tc_kernel<false, 1, 16>) : launch(retrieve_tc_kernel<false, 0, 16>);
-    } else {
-      if (measure == IA_COSINE) rc = fmt_bf16 ? launch(retrieve_tc_kernel<true, 1, 0>) : launch(retrieve_tc_kernel<true, 0, 0>);
-      else rc = fmt_bf16 ? launch(retrieve_tc_kernel<false, 1, 0>) : launch(retrieve_tc_kernel<false, 0, 0>);
-    }
-    if (rc != IA_OK) return rc;
+    if ((rc = launch_tc(cat, measure, use_kreg, tmap_q, p, grid, s)) != IA_OK) return rc;
   } else {
     auto launch = [&](auto kernel, auto* tq) -> int {
       using TP = decltype(tq);
@@ -887,6 +969,36 @@ static int catalog_topk_impl(ia_catalog* cat, int measure, float dist_eps, int d
 int ia_catalog_topk_seeded(ia_catalog* cat, int measure, const void* queries, int64_t q, int64_t ldq, int k,
                            const int64_t* tau_init, uint64_t* keys_out, ia_stream_t stream) {
   return catalog_topk_impl(cat, measure, kPdistEps, 0, queries, q, ldq, k, tau_init, keys_out, stream);
+}
+
+int ia_catalog_probe_bound(ia_catalog* cat, int measure, const void* queries, int64_t q, int64_t ldq, int kp, int groups,
+                           int64_t rows_per_group, int64_t* bound_out, ia_stream_t stream) {
+  if (cat == nullptr || queries == nullptr || bound_out == nullptr || q < 0 || ldq < cat->d) { set_error("bad arguments"); return IA_ERR_INVALID; }
+  if (measure != IA_INNER && measure != IA_COSINE) { set_error("probe: inner product / cosine only"); return IA_ERR_UNSUPPORTED; }
+  if (kp < 1 || kp > 16 || groups < 1 || rows_per_group < tc::BN || rows_per_group % tc::BN != 0 ||
+      (int64_t)groups * rows_per_group > cat->c) {
+    set_error("probe: kp in [1, 16], rows_per_group a multiple of %d, groups * rows_per_group <= catalog rows", tc::BN);
+    return IA_ERR_INVALID;
+  }
+  if (q == 0) return IA_OK;
+  if (q > 0x7FFFFFFF) { set_error("too many queries in one call"); return IA_ERR_INVALID; }
+  if (!(cat->tc_ok && ldq % 8 == 0 && reinterpret_cast<uintptr_t>(queries) % 16 == 0)) { set_error("probe: needs the tensor-core path (16-bit catalog, aligned rows)"); return IA_ERR_UNSUPPORTED; }
+  CUtensorMap tmap_q;
+  int rc;
+  if ((rc = make_tmap(&tmap_q, cat->dtype, queries, q, cat->d, ldq, tc::BM)) != IA_OK) return rc;
+  RetrParams p{};
+  p.q_rows = (int)q; p.c_rows = cat->c; p.d = (int)cat->d;
+  p.n_qt = (int)((q + tc::BM - 1) / tc::BM);
+  p.kblocks = (int)((cat->d + tc::BK - 1) / tc::BK);
+  p.row_base = cat->row_base;
+  p.flags = 14;
+  p.cinv = cat->cinv;
+  if (measure == IA_COSINE) {
+    if ((rc = grow((void**)&cat->qinv, &cat->qinv_bytes, sizeof(float) * (size_t)q)) != IA_OK) return rc;
+    if ((rc = ia_row_inv_norm(cat->dtype, queries, q, cat->d, ldq, kCosEps, cat->qinv, stream)) != IA_OK) return rc;
+    p.qinv = cat->qinv;
+  }
+  return probe_pass(cat, measure, tmap_q, p, groups, (int)(rows_per_group / tc::BN), kp, q, bound_out, (cudaStream_t)stream);
 }
 
 int ia_catalog_topk_dissimilarity(ia_catalog* cat, int p_norm, float eps, int squared, const void* queries, int64_t q,

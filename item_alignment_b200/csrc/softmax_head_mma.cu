@@ -28,6 +28,11 @@
 
 namespace ia {
 
+// cycle counters of the last launch made with IA_HEAD_DEBUG & 16 (summed over CTAs / warps): [0] forward warps waiting for rows,
+// [1] forward warps at their barrier, [2] loader warps waiting for a released stage, [3] forward warps total, [4] backward
+// warps waiting for deltas, [5] backward warps total, [6] warp 0 softmax section
+__device__ unsigned long long g_head_stats[8];
+
 namespace hmma {
 constexpr int FW = 4;            // forward warps
 constexpr int BW = 8;            // backward warps
@@ -96,7 +101,8 @@ __global__ void __launch_bounds__(hmma::THREADS, 1) softmax_head_mma_kernel(cons
   constexpr int E = 8;                 // elements per 16-byte vector
   constexpr int H = TPW * 64;          // p.h (checked by the launcher)
   constexpr int H2 = 2 * H;
-  constexpr uint32_t ROW_BYTES = H * 2u, PITCH = ROW_BYTES + 16u, STAGE_BYTES = 2u * RB * PITCH;   // [x rows | y rows]
+  constexpr uint32_t ROW_BYTES = H * 2u, PITCH = ROW_BYTES + 16u;
+  constexpr uint32_t LABEL_OFF = 2u * RB * PITCH, STAGE_BYTES = LABEL_OFF + RB * 8u;   // [x rows | y rows | 16 int64 labels]
   constexpr int VPR = H / 8;           // 16-byte vectors per row
   constexpr int STAGES = stages_for(TPW);
   float gscale = p.grad_scale;
@@ -108,7 +114,8 @@ __global__ void __launch_bounds__(hmma::THREADS, 1) softmax_head_mma_kernel(cons
   extern __shared__ __align__(128) uint8_t smem[];
   float* part = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);          // [2][FW][RB][8] partial logits
   float2* delta = reinterpret_cast<float2*>(part + 2 * FW * RB * 8);            // [STAGES][RB] (p - label, delta)
-  uint64_t* full = reinterpret_cast<uint64_t*>(delta + STAGES * RB);            // [STAGES] rows landed       (LOADERS arrivals)
+  float4* outbuf = reinterpret_cast<float4*>(delta + STAGES * RB);              // [STAGES][RB] (z0, z1, p0, p1) on their way out
+  uint64_t* full = reinterpret_cast<uint64_t*>(outbuf + STAGES * RB);           // [STAGES] rows landed       (LOADERS arrivals)
   uint64_t* dready = full + STAGES;                                             // [STAGES] delta published   (1 arrival)
   uint64_t* empty = dready + STAGES;                                            // [STAGES] backward finished (BW arrivals)
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
@@ -163,6 +170,14 @@ __global__ void __launch_bounds__(hmma::THREADS, 1) softmax_head_mma_kernel(cons
         for (int v = 0; v < VPR / 32; ++v)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)v * 512u), "l"(src + lane + 32 * v) : "memory");
       }
+      if (w == 1 && lane < RB / 2) {
+        // the group's 16 labels ride along (two per lane; bytes past the end of the array are zero-filled, never read)
+        const int64_t l0 = grp * RB + 2 * lane;
+        const int64_t have = p.n - l0;
+        const uint32_t bytes = have >= 2 ? 16u : (have == 1 ? 8u : 0u);
+        const int64_t* src = p.labels + (bytes ? l0 : 0);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(base + LABEL_OFF + (uint32_t)lane * 16u), "l"(src), "r"(bytes) : "memory");
+      }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[stage])) : "memory");
     };
     if (w >= 1) {
@@ -171,16 +186,15 @@ __global__ void __launch_bounds__(hmma::THREADS, 1) softmax_head_mma_kernel(cons
         if (grp < n_groups) issue(s, grp);
       }
     }
-    long long label_next = 0;
-    if (w == 0) {
-      const int64_t r0 = (int64_t)blockIdx.x * RB + (lane & 15);
-      label_next = r0 < p.n ? __ldg(p.labels + r0) : 0;
-    }
     int it = 0;
+    long long c_full = 0, c_bar = 0, c_empty = 0, c_soft = 0;
+    const long long c_begin = clock64();
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++it) {
       const int stage = it % STAGES;
       const uint32_t par = (uint32_t)(it / STAGES) & 1u;
+      long long c0 = clock64();
       mbar_wait(&full[stage], par);
+      c_full += clock64() - c0;
       const uint32_t tb = smem_base + (uint32_t)stage * STAGE_BYTES + tile_base + off_n;
       // partial logits of this warp's columns: D[16 pairs x 8] += tile . Wsplit.  The asm statements keep their order:
       // fragments are fetched one batch of four tiles ahead of the MMAs that consume them, and four independent accumulators
@@ -207,17 +221,18 @@ __global__ void __launch_bounds__(hmma::THREADS, 1) softmax_head_mma_kernel(cons
           make_float2((dq[0][0] + dq[1][0]) + (dq[2][0] + dq[3][0]), (dq[0][1] + dq[1][1]) + (dq[2][1] + dq[3][1]));
       *reinterpret_cast<float2*>(mypart + (g + 8) * 8 + 2 * t) =
           make_float2((dq[0][2] + dq[1][2]) + (dq[2][2] + dq[3][2]), (dq[0][3] + dq[1][3]) + (dq[2][3] + dq[3][3]));
+      c0 = clock64();
       named_bar_sync(1, FW * 32);
+      c_bar += clock64() - c0;
+      c0 = clock64();
       if (w == 0) {
-        // ---- softmax / CE / delta of the 16 pairs, one pair per lane (lanes 16-31 mirror 0-15), fixed summation order
-        const long long label = label_next;
-        {
-          const int64_t rn = (grp + gridDim.x) * RB + (lane & 15);
-          label_next = rn < p.n ? __ldg(p.labels + rn) : 0;
-        }
+        // ---- softmax / CE / delta of the 16 pairs, one pair per lane (lanes 16-31 mirror 0-15), fixed summation order.
+        // This section is the kernel's only serial chain per group, so it touches no global memory: the labels came in
+        // with the rows, logits / probs leave through shared memory (a backward warp stores them).
         const int pr = lane & 15;
         const int64_t row = grp * RB + pr;
         const bool live = row < p.n;
+        const long long label = *reinterpret_cast<const long long*>(smem + (size_t)stage * STAGE_BYTES + LABEL_OFF + pr * 8);
         const float* src = part + (size_t)((it & 1) * FW) * RB * 8 + pr * 8;
         float4 lo4[FW];
         float2 hi2[FW];
@@ -233,33 +248,45 @@ __global__ void __launch_bounds__(hmma::THREADS, 1) softmax_head_mma_kernel(cons
           z1 += (lo4[ww].y + lo4[ww].w) + hi2[ww].y;      // class 1: columns 1, 3, 5
         }
         z0 += bias0; z1 += bias1;
-        const float m = fmaxf(z0, z1);
-        const float e0 = expf(z0 - m), e1 = expf(z1 - m);
-        const float den = e0 + e1;
-        const float p0 = e0 / den, p1 = e1 / den;
+        // two-class softmax with ONE exponential: e = exp(-|z1 - z0|) in (0, 1], p_max = 1 / (1 + e), p_min = e / (1 + e),
+        // -log p[label] = log1p(e) + (label is the arg-max ? 0 : |z1 - z0|)
+        const float dz = z1 - z0, ad = fabsf(dz);
+        const float e = expf(-ad);
+        const float rden = 1.0f / (1.0f + e);
+        const float pmax = rden, pmin = e * rden;
+        const bool one_max = dz >= 0.f;
+        const float p0 = one_max ? pmin : pmax, p1 = one_max ? pmax : pmin;
         float du = 0.f;       // p - label, unscaled
         if (live) du = label != 0 ? -p0 : p1;
         if (lane < 16) {
           delta[stage * RB + pr] = make_float2(du, du * gscale);
+          outbuf[stage * RB + pr] = make_float4(z0, z1, p0, p1);
           if (live) {
-            if (p.logits) *reinterpret_cast<float2*>(p.logits + 2 * row) = make_float2(z0, z1);
-            if (p.probs) *reinterpret_cast<float2*>(p.probs + 2 * row) = make_float2(p0, p1);
-            loss_acc += logf(den) - ((label != 0 ? z1 : z0) - m);       // -log softmax[label]
+            loss_acc += log1pf(e) + (((label != 0) == one_max) ? 0.f : ad);     // -log softmax[label]
             if ((unsigned long long)label > 1ull) loss_acc = __int_as_float(0x7fc00000);   // label outside {0,1}: NaN, loudly
             db_acc += du * gscale;
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&dready[stage]);     // release: the deltas (and, transitively, the rows) are visible
+        c_soft += clock64() - c0;
       } else if (it >= 1) {
         // ---- refill the stage of the previous group once the backward warps have released it
         const int64_t gn = grp + (int64_t)(STAGES - 1) * gridDim.x;
         if (gn < n_groups) {
           const int sp = (it - 1) % STAGES;
           mbar_wait(&empty[sp], (uint32_t)((it - 1) / STAGES) & 1u);
+          c_empty += clock64() - c0;
           issue(sp, gn);
         }
       }
+    }
+    if ((p.load_mode & 16) && lane == 0) {
+      atomicAdd(&g_head_stats[0], (unsigned long long)c_full);
+      atomicAdd(&g_head_stats[1], (unsigned long long)c_bar);
+      atomicAdd(&g_head_stats[2], (unsigned long long)c_empty);
+      atomicAdd(&g_head_stats[3], (unsigned long long)(clock64() - c_begin));
+      atomicAdd(&g_head_stats[6], (unsigned long long)c_soft);
     }
   } else {
     // =========================================================================================== backward warps
@@ -293,10 +320,14 @@ __global__ void __launch_bounds__(hmma::THREADS, 1) softmax_head_mma_kernel(cons
     G* const gout = static_cast<G*>(side ? p.dy : p.dx);
     const int64_t ldg_out = side ? p.lddy : p.lddx;
     int it = 0;
+    long long c_wait = 0;
+    const long long c_begin = clock64();
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++it) {
       const int stage = it % STAGES;
       const uint32_t par = (uint32_t)(it / STAGES) & 1u;
+      const long long c0 = clock64();
       mbar_wait(&dready[stage], par);
+      c_wait += clock64() - c0;
       mbar_wait(&full[stage], par);      // already complete (the forward warps waited on it): makes the rows visible to THIS thread
       const float2* dl = delta + stage * RB;
       // ---- dW accumulators += tile^T . split(p - label): B fragment rows 2t, 2t+1, 2t+8, 2t+9, column g = term g (g < 3)
@@ -323,6 +354,14 @@ __global__ void __launch_bounds__(hmma::THREADS, 1) softmax_head_mma_kernel(cons
       float dr[RB / ROW_STEP];
 #pragma unroll
       for (int j = 0; j < RB / ROW_STEP; ++j) dr[j] = dl[j * ROW_STEP + row_par].y;
+      if (bw == 0 && lane < RB) {          // logits / probs of the group leave here, off the forward warps' serial chain
+        const float4 o = outbuf[stage * RB + lane];
+        const int64_t row = grp * RB + lane;
+        if (row < p.n) {
+          if (p.logits) *reinterpret_cast<float2*>(p.logits + 2 * row) = make_float2(o.x, o.y);
+          if (p.probs) *reinterpret_cast<float2*>(p.probs + 2 * row) = make_float2(o.z, o.w);
+        }
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);        // this warp is done with the stage's rows and deltas
       // ---- dx (or dy) of this warp's columns: one 16-byte (fp32 gradients: two) store per lane and row
@@ -340,6 +379,10 @@ __global__ void __launch_bounds__(hmma::THREADS, 1) softmax_head_mma_kernel(cons
           dst += ROW_STEP * ldg_out;
         }
       }
+    }
+    if ((p.load_mode & 16) && lane == 0) {
+      atomicAdd(&g_head_stats[4], (unsigned long long)c_wait);
+      atomicAdd(&g_head_stats[5], (unsigned long long)(clock64() - c_begin));
     }
     // ---- dW partial of this CTA (columns of this warp) -> workspace
     float* pout = reinterpret_cast<float*>(static_cast<char*>(p.workspace) + kWorkspaceBytes) + (size_t)blockIdx.x * (H2 + 2);
@@ -383,7 +426,8 @@ static int launch_mma(const HeadParams& p, cudaStream_t stream, float* dw, float
   constexpr int STAGES = stages_for(TPW);
   auto kernel = softmax_head_mma_kernel<T, G, TPW>;
   const size_t pitch = (size_t)p.h * 2 + 16;
-  const size_t smem = (size_t)STAGES * 2 * RB * pitch + sizeof(float) * 2 * FW * RB * 8 + sizeof(float2) * STAGES * RB + 8 * 3 * STAGES;
+  const size_t smem = (size_t)STAGES * (2 * RB * pitch + RB * 8) + sizeof(float) * 2 * FW * RB * 8 + (sizeof(float2) + sizeof(float4)) * STAGES * RB +
+                      8 * 3 * STAGES;
   static size_t configured[kMaxDevices] = {};
   const int slot = device_slot();
   if (smem > configured[slot]) {
@@ -394,7 +438,12 @@ static int launch_mma(const HeadParams& p, cudaStream_t stream, float* dw, float
   const int grid = (int)(groups < sm_count() ? groups : sm_count());
   HeadParams pd = p;
   static const int debug = [] { const char* e = getenv("IA_HEAD_DEBUG"); return e ? atoi(e) : 0; }();   // timing experiments only:
-  pd.load_mode = debug;                                    // 4 = skip the dW MMAs, 8 = skip the dx / dy stores (wrong results)
+  pd.load_mode = debug;                                    // 4 = skip the dW MMAs, 8 = skip the dx / dy stores (wrong results),
+  if (debug & 16) {                                        // 16 = collect the cycle counters of ia_softmax_head_last_stats
+    void* sp = nullptr;
+    IA_CUDA_CHECK(cudaGetSymbolAddress(&sp, g_head_stats));
+    IA_CUDA_CHECK(cudaMemsetAsync(sp, 0, sizeof(unsigned long long) * 8, stream));
+  }
   kernel<<<grid, THREADS, smem, stream>>>(pd);
   IA_LAUNCH_CHECK();
   if (dw || db) {
@@ -423,3 +472,9 @@ int launch_softmax_head_mma(int dtype, int grad_dtype, const HeadParams& p, cuda
 }
 
 }  // namespace ia
+
+extern "C" int ia_softmax_head_last_stats(uint64_t* out8) {
+  if (out8 == nullptr) { ia::set_error("bad arguments"); return IA_ERR_INVALID; }
+  IA_CUDA_CHECK(cudaMemcpyFromSymbol(out8, ia::g_head_stats, sizeof(unsigned long long) * 8));
+  return IA_OK;
+}

@@ -7,6 +7,7 @@ search of the BERT scripts, on the device.
 import numpy as np
 import torch
 
+from . import _lib
 from . import functional as F_
 
 
@@ -30,35 +31,31 @@ def threshold_sweep(probs, labels, thresholds=None):
 
 
 def find_best_f1_and_threshold(scores, labels, high_score_more_similar: bool = True):
-    """(best_acc, best_f1, best_precision, best_recall, threshold) as reference finetune_bert.py:72-106 computes them
-    with a Python sort + loop: stable sort by score, prefix counts, first maximum of F1 over the first n-1 cut points,
-    threshold halfway to the next score.  Done with device sort / scan primitives in float64 (same IEEE operations as
-    the Python floats of the reference)."""
+    """(best_acc, best_f1, best_precision, best_recall, threshold) as reference finetune_bert.py:72-106 computes them with a
+    Python sort + loop: stable sort by score, prefix counts, first maximum of F1 over the first n-1 cut points, threshold
+    halfway to the next score.  One C-ABI call (ia_best_f1_threshold): radix sort + scan + F1 + arg-max kernels, float64
+    arithmetic in the loop's own order; only the five results travel to the host."""
     if not scores.is_cuda:
         raise RuntimeError("item_alignment_b200 runs on CUDA tensors only (no CPU fallback)")
-    scores = scores.detach().view(-1)
-    labels = labels.to(scores.device).view(-1)
+    scores = scores.detach().reshape(-1)
+    if scores.dtype == torch.float64:
+        dt = _lib.IA_F64
+    else:
+        scores, dt = scores.to(torch.float32), _lib.IA_F32        # bf16 / fp16 scores are exact in fp32
+    scores = scores.contiguous()
+    labels = labels.to(device=scores.device, dtype=torch.int64).reshape(-1).contiguous()
     n = scores.numel()
     assert n == labels.numel()
     if n < 2:
         return 0, 0, 0, 0, 0
-    s64 = scores.to(torch.float64)
-    order = torch.sort(s64, descending=high_score_more_similar, stable=True).indices
-    ss = s64[order]
-    ll = (labels[order] == 1).to(torch.float64)
-    total_dup = float((labels.to(torch.float64)).sum())
-    neg_total = n - total_dup
-    ncorrect = torch.cumsum(ll, 0)[: n - 1]
-    nextract = torch.arange(1, n, device=scores.device, dtype=torch.float64)
-    fneg = nextract - ncorrect
-    ok = ncorrect > 0
-    precision = ncorrect / nextract
-    recall = ncorrect / total_dup if total_dup > 0 else torch.zeros_like(ncorrect)
-    f1 = torch.where(ok, 2 * precision * recall / (precision + recall), torch.zeros_like(precision))
-    f1 = torch.nan_to_num(f1, nan=0.0)
-    best = int(torch.argmax(f1))                               # first maximum, like the reference's strict '>'
-    if float(f1[best]) <= 0:
+    out = torch.empty(5, dtype=torch.float64, device=scores.device)
+    with torch.cuda.device(scores.device):
+        need = _lib.lib().ia_best_f1_workspace_bytes(n, dt)
+        ws = torch.empty(need + 256, dtype=torch.uint8, device=scores.device)
+        off = (-ws.data_ptr()) % 256
+        _lib.check(_lib.lib().ia_best_f1_threshold(dt, scores.data_ptr(), labels.data_ptr(), n, int(bool(high_score_more_similar)),
+                                                   out.data_ptr(), ws.data_ptr() + off, need, F_._stream()))
+    acc, f1, precision, recall, threshold = out.tolist()
+    if f1 <= 0:
         return 0, 0, 0, 0, 0
-    acc = (ncorrect[best] + neg_total - fneg[best]) / n
-    threshold = (ss[best] + ss[best + 1]) / 2
-    return float(acc), float(f1[best]), float(precision[best]), float(recall[best]), float(threshold)
+    return acc, f1, precision, recall, threshold

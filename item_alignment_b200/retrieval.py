@@ -87,25 +87,26 @@ class CatalogIndex:
         """(scores [Q,k] fp32, rows [Q,k] int64 global ids), best first; -1 / +-inf where fewer than k rows exist."""
         return unpack_keys(self.topk_keys(queries, k, measure), measure)
 
-    def topk_keys_probed(self, queries, k, measure="cosine", probe_fraction=1.0 / 32):
-        """EXPERIMENTAL (not measured yet, not used by default): the shard trick of ShardedCatalogIndex on one GPU.  g =
-        ceil(k / 16) disjoint row groups (probe_fraction of the catalog in total) are scanned first with k' = ceil(k / g)
-        <= 16 on the register top-k path; the smallest of their k'-th best keys is met or exceeded by >= k catalog rows,
-        so it seeds the thresholds of the main pass (ia_catalog_topk_seeded) and removes most of its cold-start list
-        insertions.  Same result as topk_keys by construction of the bound."""
-        rows = self.catalog.shape[0]
-        groups = max(1, -(-k // 16))
-        kp = -(-k // groups)
-        per = max(2048, int(rows * probe_fraction) // groups)
-        if k <= 16 or per * groups > rows:
-            return self.topk_keys(queries, k, measure)
-        words = None
-        for g in range(groups):
-            with CatalogIndex(self.catalog[g * per:(g + 1) * per], row_base=self.row_base + g * per) as probe:
-                pk = probe.topk_keys(queries, kp, measure)
-            w = (pk[:, kp - 1] >> 32) & 0xFFFFFFFF
-            words = w if words is None else torch.minimum(words, w)
-        return self.topk_keys(queries, k, measure, init_tau=words)
+    def probe_bound(self, queries, kp, groups, rows_per_group, measure="cosine"):
+        """int64 [Q] lower bounds from a probe pass over `groups` disjoint row groups (rows_per_group rows each, a multiple of
+        256) at the head of this catalog, top-kp (<= 16) per group: the smallest of the groups' kp-th best key words, 0 = none
+        (ia_catalog_probe_bound).  ia_catalog_topk runs this on its own for k > 16; shards call it to agree on a bound."""
+        if measure not in ("cosine", "inner_product"):
+            raise ValueError("probe passes exist for the tensor-core measures (cosine, inner_product)")
+        if queries.dtype != self.catalog.dtype:
+            queries = queries.to(self.catalog.dtype)
+        if queries.stride(1) != 1:
+            queries = queries.contiguous()
+        out = torch.empty(queries.shape[0], dtype=torch.int64, device=queries.device)
+        with torch.cuda.device(queries.device):
+            check(lib().ia_catalog_probe_bound(self._h, MEASURES[measure], queries.data_ptr(), queries.shape[0], _ld(queries), int(kp),
+                                               int(groups), int(rows_per_group), out.data_ptr(), _stream()))
+        return out
+
+    def topk_keys_unprobed(self, queries, k, measure="cosine"):
+        """topk_keys without the library's own probe pass (a zero bound carries no information but counts as seeded): the
+        plain cold-start scan, kept for A/B measurements and for the test that both give the same keys."""
+        return self.topk_keys(queries, k, measure, init_tau=torch.zeros(queries.shape[0], dtype=torch.int64, device=queries.device))
 
     def topk_dissimilarity(self, queries, k, p=2, eps=0.0, squared=None):
         """The k SMALLEST l1 / l2 dissimilarities per query with explicit eps / squaring: (dist [Q,k] ascending, rows).
@@ -187,46 +188,36 @@ class ShardedCatalogIndex:
             raise ValueError(f"rank {self.rank} must hold rows [{lo}, {hi}) of the catalog, got {local_catalog.shape[0]} rows")
         self.lo, self.hi = lo, hi
         self.local = CatalogIndex(local_catalog, row_base=lo) if hi > lo else None
-        # probes = disjoint row groups at the head of the local shard, scanned first with a small k' to agree on a
-        # global lower bound (probe_bound).  k' <= 16 keeps the probe on the kernel's register top-k path.
+        # probe = disjoint row groups at the head of the local shard, scanned first with a small k' to agree on a
+        # global lower bound (probe_bound)
         self.probe_fraction = probe_fraction
-        self.probes = []
-        self._probe_for = None
 
-    def _ensure_probes(self, k):
-        if self._probe_for == k or self.local is None or self.world == 1 or self.probe_fraction <= 0:
-            return
-        for p in self.probes:
-            p.close()
-        self.probes = []
+    def _probe_plan(self, k):
+        """(kp, groups, rows_per_group) of this rank's probe, or None.  k' = ceil(k / (G*g)) <= 16 keeps the probe on the
+        kernel's register top-k path; the groups cover probe_fraction of the local shard."""
+        if self.local is None or self.world == 1 or self.probe_fraction <= 0:
+            return None
         rows = self.hi - self.lo
         groups = max(1, -(-k // (16 * self.world)))
-        self.kp = -(-k // (self.world * groups))
-        per = max(2048, int(rows * self.probe_fraction) // groups)
-        if per * groups <= rows:
-            cat = self.local.catalog
-            self.probes = [CatalogIndex(cat[g * per:(g + 1) * per], row_base=self.lo + g * per) for g in range(groups)]
-        self._probe_for = k
+        kp = -(-k // (self.world * groups))
+        per = max(2048, int(rows * self.probe_fraction) // groups) // 256 * 256
+        if per * groups > rows or self.local.catalog.dtype == torch.float32:
+            return None
+        return kp, groups, per
 
     def close(self):
         if self.local is not None:
             self.local.close()
-        for p in self.probes:
-            p.close()
-        self.probes = []
 
     def probe_bound(self, queries, k, measure):
         """Lower bound on every query's final k-th best key word, agreed by all ranks with ONE small all-reduce.
         Every probe group (G ranks x g groups, disjoint rows) reports its k'-th best, k' = ceil(k / (G*g)); the
         minimum over all groups is met or exceeded by at least G*g*k' >= k catalog rows, so nothing below it can be
-        in the global top-k."""
-        self._ensure_probes(k)
-        words = None
-        for p in self.probes:
-            pk = p.topk_keys(queries, self.kp, measure)
-            w = (pk[:, self.kp - 1] >> 32) & 0xFFFFFFFF
-            words = w if words is None else torch.minimum(words, w)
-        if words is None:          # no probe on this rank (tiny or empty shard): no information, no bound
+        in the global top-k.  One launch per rank (ia_catalog_probe_bound)."""
+        plan = self._probe_plan(k) if measure in ("cosine", "inner_product") else None
+        if plan is not None:
+            words = self.local.probe_bound(queries, plan[0], plan[1], plan[2], measure)
+        else:                      # no probe on this rank (tiny, empty or fp32 shard): no information, no bound
             words = torch.zeros(queries.shape[0], dtype=torch.int64, device=queries.device)
         self.dist.all_reduce(words, op=self.dist.ReduceOp.MIN, group=self.group)
         return words

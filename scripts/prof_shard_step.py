@@ -15,21 +15,16 @@ q = torch.tanh(torch.randn(Q, D, device=dev, generator=gen)).to(torch.bfloat16)
 local = ia.CatalogIndex(cat, row_base=0)
 groups = max(1, -(-K // (16 * world)))
 kp = -(-K // (world * groups))
-per = max(2048, int(rows * frac) // groups)
+per = max(2048, int(rows * frac) // groups) // 256 * 256
 n_probe = per * groups
-probes = [ia.CatalogIndex(cat[g * per:(g + 1) * per], row_base=g * per) for g in range(groups)]
-names = ["probe topk", "bound words", "main topk (seeded)", "fake gather+merge"]
+names = ["probe bound (one launch)", "-", "main topk (seeded)", "fake gather+merge"]
 acc = {n: [] for n in names}
 tot = []
 for it in range(12):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     ev[0].record()
-    pks = [pr.topk_keys(q, kp, "cosine") for pr in probes]
+    words = local.probe_bound(q, kp, groups, per, "cosine")
     ev[1].record()
-    words = None
-    for pk in pks:
-        wd = (pk[:, kp - 1] >> 32) & 0xFFFFFFFF
-        words = wd if words is None else torch.minimum(words, wd)
     ev[2].record()
     keys = local.topk_keys(q, K, "cosine", init_tau=words)
     ev[3].record()
@@ -49,5 +44,9 @@ print(f"  total {statistics.median(tot):.3f} ms; main-pass appends/query {st['ap
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ts = []
 for it in range(8):
-    e0.record(); local.topk_keys(q, K, "cosine"); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    e0.record(); local.topk_keys_unprobed(q, K, "cosine"); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
 print(f"  unseeded main pass {statistics.median(ts[2:]):.3f} ms; appends/query {local.last_stats()['appends']/Q:.0f}")
+ts = []
+for it in range(8):
+    e0.record(); local.topk_keys(q, K, "cosine"); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+print(f"  self-probed pass (ia_catalog_topk default) {statistics.median(ts[2:]):.3f} ms; appends/query {local.last_stats()['appends']/Q:.0f}")

@@ -53,5 +53,19 @@ with tempfile.TemporaryDirectory() as td:
     ia.write_catalog(td + "/c.iacat", cat.cpu(), [str(i) for i in range(cat.shape[0])])
     with ia.CatalogFile(td + "/c.iacat") as f, f.index(100, 2900) as idx:
         idx.topk(q, 5, "cosine")
+# round 2: tensor-core softmax head (n >= 4096, h = 512), best-F1 search, probe pass + self-probed top-k, gradient recomputation
+n, d = 4100, 512
+x = torch.tanh(torch.randn(n, d, device=dev, generator=g)).to(torch.float16); y = torch.tanh(torch.randn(n, d, device=dev, generator=g)).to(torch.float16)
+l = (torch.rand(n, device=dev, generator=g) < 0.5).long()
+w = torch.randn(2, 2 * d, device=dev) * 0.02; b = torch.zeros(2, device=dev)
+F_.softmax_head_raw(x, y, w, b, l)
+xg = x.clone().requires_grad_(True)
+_, _, loss = F_.pair_score_loss("cosine", "bce", xg, y, l); (loss * 8.0).backward()
+ia.find_best_f1_and_threshold(torch.rand(20000, device=dev), (torch.rand(20000, device=dev) < 0.3).long())
+ia.find_best_f1_and_threshold(torch.rand(9000, device=dev, dtype=torch.float64), (torch.rand(9000, device=dev) < 0.3).long(), False)
+big = torch.tanh(torch.randn(40000, 128, device=dev, generator=g)).to(torch.bfloat16)
+with ia.CatalogIndex(big) as idx:
+    idx.topk_keys(q, 100, "cosine")                 # runs its own probe pass
+    idx.probe_bound(q, 13, 2, 2048, "inner_product")
 torch.cuda.synchronize()
 print("sanitize_small: done")

@@ -107,3 +107,41 @@ def test_gather_rejects_out_of_range_indices():
         assert torch.equal(sim[[0, 2]], ref)
         out = F_.pair_score_loss_gather_raw(m, "hinge", emb, emb, src, tgt, labels, check_indices=False)
         assert torch.isnan(out[2]) and torch.isfinite(out[3][[0, 2]]).all()
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+def test_best_f1_kernels_ties_tiles_and_ten_million_pairs(dt):
+    """ia_best_f1_threshold (radix sort + scan + F1 + arg-max kernels) against the oracle: tile boundaries (8192 per CTA),
+    heavy ties (stable order must be kept), both directions, degenerate inputs, and 10^7 pairs."""
+    import item_alignment_b200 as ia
+    from oracle import formula, torch_port
+    gen = torch.Generator().manual_seed(17)
+    for n, ties in ((2, False), (3, True), (255, True), (8192, False), (8193, True), (24577, True), (100_003, False)):
+        labels = (torch.rand(n, generator=gen) < 0.4).long()
+        scores = (torch.randn(n, generator=gen, dtype=torch.float64) + labels.double()).to(dt)
+        if ties:
+            scores = (torch.round(scores * 2) / 2).to(dt)          # a handful of distinct values
+        for high in (True, False):
+            ours = ia.find_best_f1_and_threshold(scores.to(DEV), labels.to(DEV), high)
+            ref = formula.best_f1_and_threshold(scores.numpy(), labels.numpy(), high)
+            assert tuple(float(v) for v in ours) == tuple(float(v) for v in ref), (n, ties, high, ours, ref)
+            if n <= 8193:
+                loop = torch_port.find_best_f1_and_threshold(scores.tolist(), labels.tolist(), high)
+                assert tuple(float(v) for v in ours) == tuple(float(v) for v in loop)
+    # all-negative labels: no cut has F1 > 0
+    assert ia.find_best_f1_and_threshold(torch.randn(5000, device=DEV).to(dt), torch.zeros(5000, dtype=torch.long, device=DEV)) == (0, 0, 0, 0, 0)
+    # 10^7 pairs with ties (bf16-rounded probabilities: ~ 10^4 distinct values)
+    n = 10_000_000
+    g = torch.Generator(device=DEV).manual_seed(23)
+    labels = (torch.rand(n, device=DEV, generator=g) < 0.2).long()
+    scores = torch.sigmoid(torch.randn(n, device=DEV, generator=g) + 2.0 * labels.float()).to(torch.bfloat16).to(dt)
+    for high in (True, False):
+        ours = ia.find_best_f1_and_threshold(scores if high else -scores, labels, high)
+        ref = formula.best_f1_and_threshold((scores if high else -scores).cpu().numpy(), labels.cpu().numpy(), high)
+        assert tuple(float(v) for v in ours) == tuple(float(v) for v in ref), (high, ours, ref)
+    torch.cuda.synchronize()
+    import time
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ia.find_best_f1_and_threshold(scores, labels, True)
+    print(f"best-F1 search over 10^7 {dt} scores: {(time.perf_counter() - t0) / 3 * 1e3:.1f} ms per call (incl. result read-back)")

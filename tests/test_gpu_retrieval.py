@@ -216,15 +216,32 @@ def test_two_gpu_sharded_retrieval_nccl(tmp_path):
     assert [open(tmp_path / f"ok{r}").read() for r in range(2)] == ["True", "True"]
 
 
-@pytest.mark.skipif(os.environ.get("IA_EXPERIMENTAL") != "1", reason="experimental path, enable with IA_EXPERIMENTAL=1")
 def test_single_gpu_probed_topk_equals_plain_topk():
-    """CatalogIndex.topk_keys_probed (probe pass + seeded thresholds on ONE GPU) must return exactly the keys of topk_keys."""
+    """ia_catalog_topk runs its own probe pass for k > 16 (1/32 of the catalog on the register top-k path seeds every item's
+    threshold): the keys must be exactly those of the plain cold-start scan, and the probe must remove list insertions.
+    Also: ia_catalog_probe_bound (the shards' entry point) returns a bound that at least k rows meet."""
     import item_alignment_b200 as ia
     gen = torch.Generator().manual_seed(31)
     cat = torch.tanh(torch.randn(200_000, 128, generator=gen)).bfloat16()
     cat[7000:7100] = cat[:100]
     q = (cat[torch.randint(0, 200_000, (300,), generator=gen)].float() + 0.05 * torch.randn(300, 128, generator=gen)).bfloat16()
+    q[:50] = cat[:50]                                    # exact ties with the duplicated rows
+    qd = q.to(DEV)
     with ia.CatalogIndex(cat.to(DEV)) as index:
         for measure in ("cosine", "inner_product"):
-            for k in (100, 40, 17):
-                assert torch.equal(index.topk_keys_probed(q.to(DEV), k, measure), index.topk_keys(q.to(DEV), k, measure))
+            for k in (100, 128, 40, 17):
+                probed = index.topk_keys(qd, k, measure)
+                a_probed = index.last_stats()["appends"]
+                plain = index.topk_keys_unprobed(qd, k, measure)
+                a_plain = index.last_stats()["appends"]
+                assert torch.equal(probed, plain), (measure, k)
+                assert a_probed < a_plain, (measure, k, a_probed, a_plain)
+            # the shards' probe: 4 groups x top-13 of 2048 rows each; >= 52 >= k = 50 rows meet the bound
+            bound = index.probe_bound(qd, 13, 4, 2048, measure)
+            keys = index.topk_keys_unprobed(qd, 50, measure)
+            assert int(bound.min()) > 0
+            assert bool((((keys[:, 49] >> 32) & 0xFFFFFFFF) >= bound).all())
+            assert torch.equal(index.topk_keys(qd, 50, measure, init_tau=bound), keys)
+    with pytest.raises(ValueError):
+        with ia.CatalogIndex(cat[:5000].to(DEV)) as small:
+            small.probe_bound(qd, 13, 4, 2048, "cosine")            # 4 x 2048 rows do not fit into 5000

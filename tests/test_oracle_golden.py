@@ -202,3 +202,21 @@ def test_eval_restatements_small_cases():
     sims, probs, loss = torch_port.gcn_pair_loop("cosine", torch.eye(3), [dict(src_idx=0, tgt_idx=0, item_label=1),
                                                                          dict(src_idx=0, tgt_idx=1, item_label=0)], "hinge", 1.0)
     assert sims.tolist() == [1.0, 0.0] and probs.tolist() == [1.0, 0.5] and float(loss) == 0.5
+
+
+def test_vectorised_best_f1_equals_the_loop_restatement():
+    """oracle/formula.best_f1_and_threshold (used to check 10^7 pairs on the GPU) == the loop restatement of
+    finetune_bert.py:72-106, ties and both sort directions included."""
+    from oracle import formula, torch_port
+    rng = np.random.default_rng(3)
+    for n, ties, dt in ((2, False, np.float64), (3, True, np.float32), (1000, False, np.float32), (2503, True, np.float64),
+                        (4000, True, np.float32)):
+        labels = (rng.random(n) < 0.35).astype(np.int64)
+        scores = (rng.standard_normal(n) + labels).astype(dt)
+        if ties:
+            scores = (np.round(scores * 3) / 3).astype(dt)
+        for high in (True, False):
+            ref = torch_port.find_best_f1_and_threshold([float(v) for v in scores], labels.tolist(), high)
+            got = formula.best_f1_and_threshold(scores, labels, high)
+            assert tuple(float(v) for v in ref) == tuple(float(v) for v in got), (n, ties, high)
+    assert formula.best_f1_and_threshold(np.zeros(5), np.zeros(5, dtype=np.int64)) == (0, 0, 0, 0, 0)     # no positives
