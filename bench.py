@@ -467,9 +467,37 @@ def bench_projection(torch, ia, device, pk):
     ms_proj = timed_us(torch, lambda: F_.project_tanh_raw(f1, f2, w, b), 20, 3) / 1e3
     ms_lib = timed_us(torch, library, 20, 3) / 1e3
     tf = 2.0 * 2 * n * k * h / (ms_score * 1e-3) / 1e12
+    # training step of the head (train() mode, dropout 0.1): projection + cosine score + bce + the whole backward
+    labels = (torch.rand(n, device=device, generator=gen) < 0.5).long()
+    g1, g2 = f1.clone().requires_grad_(True), f2.clone().requires_grad_(True)
+    wm, bm = w.float().requires_grad_(True), b.clone().requires_grad_(True)      # fp32 master weights, cast per step like autocast
+    step_no = [0]
+
+    def ours_train():
+        step_no[0] += 1
+        _, _, _, _, loss = F_.project_score_loss_train("cosine", "bce", g1, g2, wm, bm, labels, 0.1, SEED, step_no[0])
+        loss.backward()
+        g1.grad = g2.grad = wm.grad = bm.grad = None
+
+    def library_train():
+        drop = torch.nn.functional.dropout
+        w16, b16 = wm.to(torch.bfloat16), bm.to(torch.bfloat16)
+        x = drop(torch.tanh(torch.nn.functional.linear(drop(g1, 0.1), w16, b16)), 0.1)
+        y = drop(torch.tanh(torch.nn.functional.linear(drop(g2, 0.1), w16, b16)), 0.1)
+        s = torch.nn.functional.cosine_similarity(x.float(), y.float())
+        torch.nn.functional.binary_cross_entropy_with_logits(s, labels.float()).backward()
+        g1.grad = g2.grad = wm.grad = bm.grad = None
+
+    ms_train = timed_us(torch, ours_train, 10, 3) / 1e3
+    ms_train_lib = timed_us(torch, library_train, 10, 3) / 1e3
+    tf_train = 3 * 2.0 * 2 * n * k * h / (ms_train * 1e-3) / 1e12          # forward + data-gradient + weight-gradient GEMMs
     return {"workload": "tanh(dense(f)) both sides + cosine score + probability in one launch, 65536 pairs, K = H = 1024 bf16",
             "Mpairs_s": r3(n / ms_score / 1e3), "ms": r3(ms_score), "tf": r3(tf), "frac_sustained": r3(tf / pk["tf_sustained"]),
-            "projection_only_ms": r3(ms_proj), "library_linear_tanh_cosine_ms": r3(ms_lib)}
+            "projection_only_ms": r3(ms_proj), "library_linear_tanh_cosine_ms": r3(ms_lib),
+            "train_step": {"workload": "train() mode, dropout 0.1: dropout + GEMM(bias, tanh, dropout) + fused cosine/bce loss writing d_pre + "
+                                       "dgrad GEMM + MN-major wgrad GEMM + db, gradients for f1, f2, W, b",
+                           "ms": r3(ms_train), "tf": r3(tf_train), "frac_sustained": r3(tf_train / pk["tf_sustained"]),
+                           "library_autograd_ms": r3(ms_train_lib)}}
 
 
 def main():
@@ -642,7 +670,8 @@ def main():
                              "oracle_ok": bool(c5["oracle_slab"]["scores_ok"] and c5["oracle_slab"]["rows_ok_where_separated"])}
         if projection:
             summary["projection"] = {"ms": projection["ms"], "frac_sustained": projection["frac_sustained"],
-                                     "library_ms": projection["library_linear_tanh_cosine_ms"]}
+                                     "library_ms": projection["library_linear_tanh_cosine_ms"],
+                                     "train_step_ms": projection["train_step"]["ms"], "train_step_library_ms": projection["train_step"]["library_autograd_ms"]}
         line = {
             "metric": "pairs/s (fused score+loss fwd/bwd)", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

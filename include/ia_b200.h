@@ -84,6 +84,19 @@ int ia_pair_score_loss_fwd_bwd(int measure, int loss, float margin, int reductio
                                float grad_scale, const float* upstream_dev, int skip_if_one, void* workspace,
                                size_t workspace_bytes, ia_stream_t stream);
 
+/* The same launch with the backward of the head's activation folded into the gradient store (training path of the head
+ * projection, base.py:67-75): x, y are the head's OUTPUTS drop(tanh(dense(.))) and, with act_bwd_scale = 1/(1-p) (1.0 = no
+ * dropout; 0 = plain gradients, identical to ia_pair_score_loss_fwd_bwd), dx / dy receive
+ *     d_pre = dL/d(out) * keep/(1-p) * (1 - tanh^2)      -- the gradient w.r.t. the dense layer's output,
+ * ready for ia_project_dgrad / ia_project_wgrad: no separate pass over the [n, h] gradients.  With dropout active a dropped
+ * element is recognised by its exact zero. */
+int ia_pair_score_loss_act_bwd(int measure, int loss, float margin, int reduction, int dtype,
+                               int grad_dtype, const void* x, const void* y, int64_t ldx, int64_t ldy,
+                               const int64_t* labels, int64_t n, int64_t d, float* sim, float* probs,
+                               float* loss_out, void* dx, void* dy, int64_t lddx, int64_t lddy,
+                               float grad_scale, const float* upstream_dev, int skip_if_one, float act_bwd_scale,
+                               void* workspace, size_t workspace_bytes, ia_stream_t stream);
+
 /* ---- backward of the score alone (upstream gradient is an arbitrary per-pair vector) ----------
  * Replaces autograd of InnerProduct / CosineSimilarity / PairwiseDistance when the caller keeps the
  * reference's unfused head -> loss module sequence.  gsim: [n] fp32 = dL/dsim. */
@@ -189,6 +202,44 @@ int ia_project_score_fwd(int measure, int dtype, const void* f1, const void* f2,
                          void* x, void* y, int64_t ldx, int64_t ldy, float* sim, float* probs,
                          double threshold, uint8_t* labels_out, int fast_tanh, void* workspace,
                          size_t workspace_bytes, ia_stream_t stream);
+
+/* ---- training side of the head projection: x = drop(tanh(dense(drop(f)))) and its backward ---------------------------
+ * Replaces VecSimClassificationHead.forward in train() mode (src/models/base.py:50-53,67-75: nn.Dropout on the features and on
+ * the tanh outputs) and the autograd backward of dense / tanh / dropout, for bf16 / fp16 tensors.  Dropout masks are
+ * counter-based (Philox4x32-10): element (row, col) of a [rows, cols] tensor is kept iff the 16-bit lane (row & 7) of
+ * philox(key = seed, counter = ((row >> 3) * cols + col, stream, step)) is >= round(p * 2^16); kept values are scaled by
+ * 1/(1-p).  streams: 0 = f1, 1 = f2, 2 = x, 3 = y; `step` is the caller's call counter.  (torch's own RNG stream cannot be
+ * reproduced inside a GEMM epilogue; the masks are replayed on the host by the tests.)
+ *   ia_dropout_fwd                out = x * mask / (1 - p)                (input dropout of one side; cols % 8 == 0)
+ *   ia_project_tanh_dropout_fwd   one tcgen05 GEMM for both sides, bias + tanh + OUTPUT dropout in its epilogue; f1, f2 are the
+ *                                 already dropped features.  p_drop = 0 is ia_project_tanh_fwd.
+ *   ia_tanh_dropout_bwd           d_pre = g * [out != 0 or no dropout] * s * (1 - (out / s)^2), s = keep_scale = 1/(1-p)
+ *                                 (0 or 1: no dropout) -- for an arbitrary upstream gradient g; the fused pair-loss launch
+ *                                 ia_pair_score_loss_act_bwd writes d_pre itself
+ *   ia_transpose16                dst[c][r] = src[r][c] for 16-bit elements (W -> W^T once per step for the data gradient)
+ *   ia_project_dgrad              df1, df2 = (d_pre . W) * input mask / (1 - p): the forward GEMM kernel on (d_pre, W^T [k_in, h])
+ *                                 with the input-dropout mask (streams 0, 1) in its epilogue
+ *   ia_project_wgrad              dW [h, k_in] fp32 = d_pre1^T f1' + d_pre2^T f2' (f' = the dropped features), db [h] fp32 =
+ *                                 column sums of d_pre1, d_pre2 (NULL: skipped): a tcgen05 GEMM contracting over the ROWS
+ *                                 (MN-major operands), split-K with a fixed-order reduce.  workspace:
+ *                                 ia_project_wgrad_workspace_bytes(n, h, k_in) bytes, 256-byte aligned. */
+int ia_dropout_fwd(int dtype, const void* x, int64_t ldx, int64_t rows, int64_t cols, float p_drop, uint64_t seed,
+                   uint32_t step, uint32_t stream_id, void* out, int64_t ldo, ia_stream_t stream);
+int ia_project_tanh_dropout_fwd(int dtype, const void* f1, const void* f2, int64_t ldf1, int64_t ldf2, int64_t n,
+                                int64_t k_in, const void* w, int64_t ldw, const float* bias, int64_t h, void* x,
+                                void* y, int64_t ldx, int64_t ldy, float p_drop, uint64_t seed, uint32_t step,
+                                ia_stream_t stream);
+int ia_tanh_dropout_bwd(int dtype, const void* g, int64_t ldg, const void* out, int64_t ldo, int64_t rows,
+                        int64_t cols, float keep_scale, void* dpre, int64_t ldd, ia_stream_t stream);
+int ia_transpose16(const void* src, int64_t rows, int64_t cols, int64_t lds, void* dst, int64_t ldd,
+                   ia_stream_t stream);
+int ia_project_dgrad(int dtype, const void* d1, const void* d2, int64_t ldd1, int64_t ldd2, int64_t n, int64_t h,
+                     const void* wt, int64_t ldwt, int64_t k_in, void* df1, void* df2, int64_t lddf1,
+                     int64_t lddf2, float p_drop, uint64_t seed, uint32_t step, ia_stream_t stream);
+size_t ia_project_wgrad_workspace_bytes(int64_t n, int64_t h, int64_t k_in);
+int ia_project_wgrad(int dtype, const void* d1, const void* d2, int64_t ldd, const void* f1, const void* f2,
+                     int64_t ldf, int64_t n, int64_t h, int64_t k_in, float* dw, float* db, void* workspace,
+                     size_t workspace_bytes, ia_stream_t stream);
 
 /* ---- row inverse norms: 1 / max(||row||, eps) (cosine retrieval pre-pass, base.py:58 eps) ------ */
 int ia_row_inv_norm(int dtype, const void* x, int64_t n, int64_t d, int64_t ldx, float eps,

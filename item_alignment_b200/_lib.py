@@ -5,7 +5,7 @@ fallback: if the CUDA library is missing or an entry point fails, the product ra
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libia_b200.so")
@@ -31,6 +31,19 @@ SIGNATURES = {
     "ia_pair_score_loss_fwd_bwd": (c_int, [c_int, c_int, c_float, c_int, c_int, c_int, c_void_p, c_void_p, c_int64,
                                            c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_int64, c_int64, c_float, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "ia_pair_score_loss_act_bwd": (c_int, [c_int, c_int, c_float, c_int, c_int, c_int, c_void_p, c_void_p, c_int64,
+                                           c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_int64, c_int64, c_float, c_void_p, c_int, c_float, c_void_p, c_size_t, c_void_p]),
+    "ia_dropout_fwd": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int64, c_float, c_uint64, c_uint32, c_uint32, c_void_p, c_int64, c_void_p]),
+    "ia_project_tanh_dropout_fwd": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p,
+                                            c_int64, c_void_p, c_void_p, c_int64, c_int64, c_float, c_uint64, c_uint32, c_void_p]),
+    "ia_tanh_dropout_bwd": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_int64, c_void_p]),
+    "ia_transpose16": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
+    "ia_project_dgrad": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
+                                 c_void_p, c_int64, c_int64, c_float, c_uint64, c_uint32, c_void_p]),
+    "ia_project_wgrad_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "ia_project_wgrad": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p,
+                                 c_void_p, c_void_p, c_size_t, c_void_p]),
     "ia_pair_score_bwd": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
                                   c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "ia_pair_score_gather_fwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p,

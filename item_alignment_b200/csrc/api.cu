@@ -206,6 +206,17 @@ int ia_pair_score_loss_fwd_bwd(int measure, int loss, float margin, int reductio
                                int64_t n, int64_t d, float* sim, float* probs, float* loss_out, void* dx, void* dy,
                                int64_t lddx, int64_t lddy, float grad_scale, const float* upstream_dev,
                                int skip_if_one, void* workspace, size_t workspace_bytes, ia_stream_t stream) {
+  return ia_pair_score_loss_act_bwd(measure, loss, margin, reduction, dtype, grad_dtype, x, y, ldx, ldy, labels, n, d, sim, probs, loss_out,
+                                    dx, dy, lddx, lddy, grad_scale, upstream_dev, skip_if_one, 0.0f, workspace, workspace_bytes, stream);
+}
+
+int ia_pair_score_loss_act_bwd(int measure, int loss, float margin, int reduction, int dtype, int grad_dtype,
+                               const void* x, const void* y, int64_t ldx, int64_t ldy, const int64_t* labels,
+                               int64_t n, int64_t d, float* sim, float* probs, float* loss_out, void* dx, void* dy,
+                               int64_t lddx, int64_t lddy, float grad_scale, const float* upstream_dev,
+                               int skip_if_one, float act_bwd_scale, void* workspace, size_t workspace_bytes,
+                               ia_stream_t stream) {
+  if (!(act_bwd_scale >= 0.f)) { set_error("act_bwd_scale must be 0 (off) or the dropout keep scale 1/(1-p) >= 1"); return IA_ERR_INVALID; }
   int rc = check_common(measure, dtype, x, y, n, d, ldx, ldy);
   if (rc != IA_OK) return rc;
   if (loss < IA_LOSS_BCE || loss > IA_LOSS_COSINE) { set_error("unsupported loss_type %d", loss); return IA_ERR_INVALID; }
@@ -237,7 +248,7 @@ int ia_pair_score_loss_fwd_bwd(int measure, int loss, float margin, int reductio
   p.loss_scale = reduction == IA_RED_MEAN ? 1.0 / (double)n : 1.0;
   p.grad_scale = reduction == IA_RED_MEAN ? (float)((double)grad_scale / (double)n) : grad_scale;
   p.workspace = workspace;
-  p.upstream = upstream_dev; p.upstream_skip_one = skip_if_one;
+  p.upstream = upstream_dev; p.upstream_skip_one = skip_if_one; p.act_bwd = act_bwd_scale;
   return dispatch_pair(kModeFused, loss == IA_LOSS_COSINE, measure, dtype, grad_dtype, p, (cudaStream_t)stream);
 }
 

@@ -47,6 +47,9 @@ struct PairParams {
   int64_t rows_x, rows_y;      // gather: rows of the embedding matrices; an index outside [0, rows) poisons that pair with NaN
   const float* upstream;       // fused: optional DEVICE scalar d(total)/d(loss) folded into the gradients (autograd backward)
   int upstream_skip_one;       // with upstream: leave at once when *upstream == 1 (the gradients already in dx, dy are exact)
+  float act_bwd;               // 0: dx, dy are gradients w.r.t. x, y.  > 0: x, y are tanh outputs after nn.Dropout with keep scale
+                               // act_bwd = 1/(1-p) (1 = no dropout) and the kernel writes d_pre = g * keep * scale * (1 - t^2),
+                               // the gradient w.r.t. the dense layer's output (head projection backward, base.py:67-75)
 };
 
 // Per-pair sums gathered in one sweep over the registers.
@@ -318,6 +321,18 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
                 gy[j] = -gx[j];
               }
             }
+            if (p.act_bwd > 0.f) {
+              // tanh (and dropout) backward fused into the store: t = out / scale where kept; with dropout active a dropped
+              // element is recognised by its exact zero (a kept tanh value is 0 only for a pre-activation of exactly 0)
+              const float sc = p.act_bwd, inv = 1.0f / p.act_bwd;
+              const bool drop = p.act_bwd != 1.0f;
+#pragma unroll
+              for (int j = 0; j < E; ++j) {
+                const float tx = fx[j] * inv, ty = fy[j] * inv;
+                gx[j] = (drop && fx[j] == 0.f) ? 0.f : gx[j] * sc * (1.0f - tx * tx);
+                gy[j] = (drop && fy[j] == 0.f) ? 0.f : gy[j] * sc * (1.0f - ty * ty);
+              }
+            }
             Packer<G, E>::store(dxr + (int64_t)v * E, gx);
             Packer<G, E>::store(dyr + (int64_t)v * E, gy);
           }
@@ -420,6 +435,13 @@ __global__ void __launch_bounds__(256) pair_kernel_generic(const PairParams p) {
         } else {
           gx = c.A * (fx - fy + kPdistEps);
           gy = -gx;
+        }
+        if (p.act_bwd > 0.f) {
+          const float sc = p.act_bwd, inv = 1.0f / p.act_bwd;
+          const bool drop = p.act_bwd != 1.0f;
+          const float tx = fx * inv, ty = fy * inv;
+          gx = (drop && fx == 0.f) ? 0.f : gx * sc * (1.0f - tx * tx);
+          gy = (drop && fy == 0.f) ? 0.f : gy * sc * (1.0f - ty * ty);
         }
         dxr[j] = from_float<G>(gx);
         dyr[j] = from_float<G>(gy);

@@ -19,6 +19,7 @@
 #include <type_traits>
 
 #include "pair_kernels.cuh"
+#include "philox.cuh"
 #include "ptx_sm100.cuh"
 
 namespace ia {
@@ -35,6 +36,9 @@ constexpr int SUMS_BYTES = 4 * BM * 16;   // per epilogue warp: one float4 of ro
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SUMS_BYTES + 256 + 1024;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 constexpr int kNoScore = -1;
+// epilogue of the GEMM: bias + tanh (inference), bias + tanh + output dropout (training forward), or nothing but the INPUT
+// dropout mask (the same kernel computing df = (d_pre . W) * mask / (1 - p), the data gradient of the projection)
+enum Epilogue { kEpiTanh = 0, kEpiTanhDropout = 1, kEpiMask = 2 };
 }  // namespace proj
 
 struct ProjParams {
@@ -47,6 +51,7 @@ struct ProjParams {
   unsigned long long* stats;   // optional cycle counters (diagnostics): MMA waits on TMA / on the epilogue, epilogue waits
   int debug_flags;
   float4* sums;        // SCORE: [parts * 4 column quarters][n] partial (xy, xx, yy, dist)
+  DropoutParams drop;  // kEpiTanhDropout: mask of the OUTPUTS (streams 2, 3); kEpiMask: mask of the inputs f1, f2 (streams 0, 1)
 };
 
 // tanh to ~1e-6 relative (the output is rounded to 8 or 11 mantissa bits right after): 1 - 2/(e^{2a}+1) away from
@@ -104,7 +109,7 @@ template <> __device__ __forceinline__ float round_to<__half>(float v, unsigned 
 // The accumulator is held TRANSPOSED: TMEM lane = output column (a row of W, the M operand), TMEM column = pair row
 // (columns 0-127: f1 rows -> x, 128-255: f2 rows -> y; [f1 tile; f2 tile] is one 256-row N operand).  One N=256 MMA per
 // K step moves 12 KB of operands per 128 tensor-core cycles (two N=128 MMAs would move 16 KB: shared-memory bound).
-template <typename T, int MEASURE, bool FAST>
+template <typename T, int MEASURE, bool FAST, int EPI>
 __global__ void __launch_bounds__(proj::THREADS, 1)
 project_kernel(const __grid_constant__ CUtensorMap tmap_f1, const __grid_constant__ CUtensorMap tmap_f2,
                const __grid_constant__ CUtensorMap tmap_w, const ProjParams p) {
@@ -241,10 +246,48 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_f1, const __grid_constan
           // all 64 tanh chains first, branch-free (the scheduler interleaves them), then the stores
           unsigned short bx[32], by[32];
           float fx[32], fy[32];
+          if (EPI == kEpiMask) {
+            // data gradient: df = acc * (input-dropout mask / (1 - p)); identity when dropout is off
+            uint32_t kx = 0xffffffffu, ky = 0xffffffffu;
+            if (p.drop.thr16 != 0) {
+              kx = 0u; ky = 0u;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            fx[i] = round_to<T>(tanh_sel<FAST>(__uint_as_float(rx[i]) + bias), bx[i]);
-            fy[i] = round_to<T>(tanh_sel<FAST>(__uint_as_float(ry[i]) + bias), by[i]);
+              for (int q = 0; q < 4; ++q) {
+                kx |= dropout_keep8(p.drop, 0u, (uint64_t)(r_base >> 3) + q, (uint32_t)p.h, (uint32_t)(col_ok ? col : 0)) << (8 * q);
+                ky |= dropout_keep8(p.drop, 1u, (uint64_t)(r_base >> 3) + q, (uint32_t)p.h, (uint32_t)(col_ok ? col : 0)) << (8 * q);
+              }
+            }
+            const float sc = p.drop.thr16 != 0 ? p.drop.scale : 1.0f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              fx[i] = round_to<T>(((kx >> i) & 1u) ? __uint_as_float(rx[i]) * sc : 0.f, bx[i]);
+              fy[i] = round_to<T>(((ky >> i) & 1u) ? __uint_as_float(ry[i]) * sc : 0.f, by[i]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              fx[i] = tanh_sel<FAST>(__uint_as_float(rx[i]) + bias);
+              fy[i] = tanh_sel<FAST>(__uint_as_float(ry[i]) + bias);
+            }
+            if (EPI == kEpiTanhDropout) {
+              // nn.Dropout on the tanh outputs (base.py:70,75): keep * 1/(1-p), masks of streams 2 (x) and 3 (y)
+              uint32_t kx = 0u, ky = 0u;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                kx |= dropout_keep8(p.drop, 2u, (uint64_t)(r_base >> 3) + q, (uint32_t)p.h, (uint32_t)(col_ok ? col : 0)) << (8 * q);
+                ky |= dropout_keep8(p.drop, 3u, (uint64_t)(r_base >> 3) + q, (uint32_t)p.h, (uint32_t)(col_ok ? col : 0)) << (8 * q);
+              }
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                fx[i] = ((kx >> i) & 1u) ? fx[i] * p.drop.scale : 0.f;
+                fy[i] = ((ky >> i) & 1u) ? fy[i] * p.drop.scale : 0.f;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              fx[i] = round_to<T>(fx[i], bx[i]);
+              fy[i] = round_to<T>(fy[i], by[i]);
+            }
           }
           // a warp writes 32 consecutive columns of one row per store: 64 contiguous bytes
           const int rows_here = col_ok ? (int)min((int64_t)32, p.n - r_base) : 0;
@@ -372,10 +415,10 @@ static int make_plan(int64_t n, int64_t k_in, int64_t h, ProjPlan* pl) {
   return IA_OK;
 }
 
-template <typename T, int MEASURE, bool FAST>
+template <typename T, int MEASURE, bool FAST, int EPI = proj::kEpiTanh>
 static int launch_project(const CUtensorMap& m1, const CUtensorMap& m2, const CUtensorMap& mw, const ProjParams& p, int ctas,
                           cudaStream_t st) {
-  auto kern = project_kernel<T, MEASURE, FAST>;
+  auto kern = project_kernel<T, MEASURE, FAST, EPI>;
   static bool configured[kMaxDevices] = {};   // per instantiation and device (function attributes are per context)
   const int slot = device_slot();
   if (!configured[slot]) {
@@ -389,8 +432,10 @@ static int launch_project(const CUtensorMap& m1, const CUtensorMap& m2, const CU
 }
 
 template <typename T, bool FAST>
-static int project_dispatch(int measure, const CUtensorMap& m1, const CUtensorMap& m2, const CUtensorMap& mw, const ProjParams& p,
+static int project_dispatch(int measure, int epi, const CUtensorMap& m1, const CUtensorMap& m2, const CUtensorMap& mw, const ProjParams& p,
                             int ctas, cudaStream_t st) {
+  if (epi == proj::kEpiTanhDropout) return launch_project<T, proj::kNoScore, false, proj::kEpiTanhDropout>(m1, m2, mw, p, ctas, st);
+  if (epi == proj::kEpiMask) return launch_project<T, proj::kNoScore, false, proj::kEpiMask>(m1, m2, mw, p, ctas, st);
   switch (measure) {
     case proj::kNoScore: return launch_project<T, proj::kNoScore, FAST>(m1, m2, mw, p, ctas, st);
     case IA_INNER: return launch_project<T, IA_INNER, FAST>(m1, m2, mw, p, ctas, st);
@@ -412,7 +457,7 @@ static unsigned long long* proj_stats_buffer() {
   return g_proj_stats[dev];
 }
 
-static int project_common(int measure, int fast_tanh, int dtype, const void* f1, const void* f2, int64_t ldf1, int64_t ldf2, int64_t n,
+static int project_common(int measure, int epi, const DropoutParams& drop, int fast_tanh, int dtype, const void* f1, const void* f2, int64_t ldf1, int64_t ldf2, int64_t n,
                           int64_t k_in, const void* w, int64_t ldw, const float* bias, int64_t h, void* x, void* y, int64_t ldx,
                           int64_t ldy, float4* sums, const ProjPlan& pl, cudaStream_t st) {
   if (dtype != IA_BF16 && dtype != IA_F16) {
@@ -445,12 +490,12 @@ static int project_common(int measure, int fast_tanh, int dtype, const void* f1,
     p.stats = (p.debug_flags & 2) ? proj_stats_buffer() : nullptr;
     if (p.stats != nullptr) IA_CUDA_CHECK(cudaMemsetAsync(p.stats, 0, 8 * sizeof(unsigned long long), st));
   }
-  p.cts_per_part = pl.cts_per_part; p.bias = bias; p.x = x; p.y = y; p.ldx = ldx; p.ldy = ldy; p.sums = sums;
-  if (fast_tanh)
-    return dtype == IA_BF16 ? project_dispatch<__nv_bfloat16, true>(measure, m1, m2, mw, p, pl.ctas, st)
-                            : project_dispatch<__half, true>(measure, m1, m2, mw, p, pl.ctas, st);
-  return dtype == IA_BF16 ? project_dispatch<__nv_bfloat16, false>(measure, m1, m2, mw, p, pl.ctas, st)
-                          : project_dispatch<__half, false>(measure, m1, m2, mw, p, pl.ctas, st);
+  p.cts_per_part = pl.cts_per_part; p.bias = bias; p.x = x; p.y = y; p.ldx = ldx; p.ldy = ldy; p.sums = sums; p.drop = drop;
+  if (fast_tanh && epi == proj::kEpiTanh)
+    return dtype == IA_BF16 ? project_dispatch<__nv_bfloat16, true>(measure, epi, m1, m2, mw, p, pl.ctas, st)
+                            : project_dispatch<__half, true>(measure, epi, m1, m2, mw, p, pl.ctas, st);
+  return dtype == IA_BF16 ? project_dispatch<__nv_bfloat16, false>(measure, epi, m1, m2, mw, p, pl.ctas, st)
+                          : project_dispatch<__half, false>(measure, epi, m1, m2, mw, p, pl.ctas, st);
 }
 
 }  // namespace ia
@@ -467,8 +512,44 @@ int ia_project_tanh_fwd(int dtype, const void* f1, const void* f2, int64_t ldf1,
   int rc = make_plan(n, k_in, h, &pl);
   if (rc != IA_OK) return rc;
   if (x == nullptr || y == nullptr) { set_error("projection: null output"); return IA_ERR_INVALID; }
-  return project_common(proj::kNoScore, fast_tanh, dtype, f1, f2, ldf1, ldf2, n, k_in, w, ldw, bias, h, x, y, ldx, ldy, nullptr, pl,
-                        (cudaStream_t)stream);
+  return project_common(proj::kNoScore, proj::kEpiTanh, DropoutParams{}, fast_tanh, dtype, f1, f2, ldf1, ldf2, n, k_in, w, ldw, bias, h, x, y,
+                        ldx, ldy, nullptr, pl, (cudaStream_t)stream);
+}
+
+static int make_dropout(float p, uint64_t seed, uint32_t step, DropoutParams* d) {
+  if (!(p >= 0.f) || !(p < 1.f)) { set_error("dropout probability must be in [0, 1)"); return IA_ERR_INVALID; }
+  d->seed_lo = (uint32_t)seed; d->seed_hi = (uint32_t)(seed >> 32); d->step = step;
+  d->thr16 = dropout_threshold16(p);
+  d->scale = 1.0f / (1.0f - p);
+  return IA_OK;
+}
+
+int ia_project_tanh_dropout_fwd(int dtype, const void* f1, const void* f2, int64_t ldf1, int64_t ldf2, int64_t n, int64_t k_in,
+                                const void* w, int64_t ldw, const float* bias, int64_t h, void* x, void* y, int64_t ldx, int64_t ldy,
+                                float p_drop, uint64_t seed, uint32_t step, ia_stream_t stream) {
+  if (n == 0) return IA_OK;
+  ProjPlan pl;
+  int rc = make_plan(n, k_in, h, &pl);
+  if (rc != IA_OK) return rc;
+  if (x == nullptr || y == nullptr) { set_error("projection: null output"); return IA_ERR_INVALID; }
+  DropoutParams d;
+  if ((rc = make_dropout(p_drop, seed, step, &d)) != IA_OK) return rc;
+  return project_common(proj::kNoScore, d.thr16 ? proj::kEpiTanhDropout : proj::kEpiTanh, d, 0, dtype, f1, f2, ldf1, ldf2, n, k_in, w, ldw,
+                        bias, h, x, y, ldx, ldy, nullptr, pl, (cudaStream_t)stream);
+}
+
+int ia_project_dgrad(int dtype, const void* d1, const void* d2, int64_t ldd1, int64_t ldd2, int64_t n, int64_t h, const void* wt,
+                     int64_t ldwt, int64_t k_in, void* df1, void* df2, int64_t lddf1, int64_t lddf2, float p_drop, uint64_t seed,
+                     uint32_t step, ia_stream_t stream) {
+  if (n == 0) return IA_OK;
+  ProjPlan pl;
+  int rc = make_plan(n, h, k_in, &pl);      // contraction over h, k_in output columns
+  if (rc != IA_OK) return rc;
+  if (df1 == nullptr || df2 == nullptr) { set_error("projection: null output"); return IA_ERR_INVALID; }
+  DropoutParams d;
+  if ((rc = make_dropout(p_drop, seed, step, &d)) != IA_OK) return rc;
+  return project_common(proj::kNoScore, proj::kEpiMask, d, 0, dtype, d1, d2, ldd1, ldd2, n, h, wt, ldwt, nullptr, k_in, df1, df2, lddf1,
+                        lddf2, nullptr, pl, (cudaStream_t)stream);
 }
 
 int ia_project_last_stats(uint64_t* out8) {
@@ -503,7 +584,7 @@ int ia_project_score_fwd(int measure, int dtype, const void* f1, const void* f2,
     return IA_ERR_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  rc = project_common(measure, fast_tanh, dtype, f1, f2, ldf1, ldf2, n, k_in, w, ldw, bias, h, x, y, ldx, ldy,
+  rc = project_common(measure, proj::kEpiTanh, DropoutParams{}, fast_tanh, dtype, f1, f2, ldf1, ldf2, n, k_in, w, ldw, bias, h, x, y, ldx, ldy,
                       reinterpret_cast<float4*>(workspace), pl, st);
   if (rc != IA_OK) return rc;
   const unsigned blocks = (unsigned)((n + 255) / 256);

@@ -403,6 +403,203 @@ def project_score_raw(measure, f1, f2, w, b, threshold=None, want_embeds=False, 
     return sim, probs, labels, x, y
 
 
+# ------------------------------------------------------------------------------------------- projection, training side
+def _keep_scale(p):
+    return 1.0 / (1.0 - float(p)) if p > 0 else 1.0
+
+
+def dropout_raw(x, p, seed, step, stream_id):
+    """out = x * mask / (1 - p) with the counter-based masks of csrc/philox.cuh (stream_id 0: f1, 1: f2)."""
+    if x.dtype not in (torch.bfloat16, torch.float16) or x.dim() != 2 or x.shape[1] % 8 != 0:
+        raise NotImplementedError("the dropout kernel runs [rows, cols] bf16 / fp16 tensors with cols % 8 == 0")
+    x = x if (x.stride(1) == 1 and x.stride(0) % 8 == 0 and x.data_ptr() % 16 == 0) else x.contiguous()
+    out = torch.empty_like(x, memory_format=torch.contiguous_format)
+    with torch.cuda.device(x.device):
+        check(lib().ia_dropout_fwd(_DT[x.dtype], x.data_ptr(), _ld(x), x.shape[0], x.shape[1], float(p), int(seed), int(step), int(stream_id),
+                                   out.data_ptr(), out.shape[1], _stream()))
+    return out
+
+
+def project_tanh_dropout_raw(f1d, f2d, w, b, p, seed, step):
+    """x, y = drop(tanh(f @ w.T + b)) for both sides from ONE tcgen05 GEMM launch, output dropout in the epilogue (streams 2, 3).
+    f1d, f2d are the (already dropped) features."""
+    f1d, f2d, w, b = _prep_project(f1d, f2d, w, b)
+    n, k = f1d.shape
+    h = w.shape[0]
+    x = torch.empty((n, h), dtype=f1d.dtype, device=f1d.device)
+    y = torch.empty((n, h), dtype=f1d.dtype, device=f1d.device)
+    with torch.cuda.device(f1d.device):
+        check(lib().ia_project_tanh_dropout_fwd(_DT[f1d.dtype], f1d.data_ptr(), f2d.data_ptr(), _ld(f1d), _ld(f2d), n, k, w.data_ptr(), _ld(w),
+                                                b.data_ptr() if b is not None else None, h, x.data_ptr(), y.data_ptr(), h, h, float(p),
+                                                int(seed), int(step), _stream()))
+    return x, y
+
+
+def tanh_dropout_bwd_raw(g, out, p):
+    """d_pre = g * keep / (1 - p) * (1 - tanh^2) from the head's output `out` = drop(tanh(.)) and an upstream gradient g."""
+    g = g.to(out.dtype).contiguous()
+    dpre = torch.empty_like(out, memory_format=torch.contiguous_format)
+    with torch.cuda.device(out.device):
+        check(lib().ia_tanh_dropout_bwd(_DT[out.dtype], g.data_ptr(), g.shape[1], out.data_ptr(), _ld(out), out.shape[0], out.shape[1],
+                                        _keep_scale(p), dpre.data_ptr(), dpre.shape[1], _stream()))
+    return dpre
+
+
+def transpose16_raw(w):
+    """w [h, k] -> w.T materialised [k, h] (16-bit); the data-gradient GEMM wants the contraction dimension contiguous."""
+    w = w.contiguous()
+    wt = torch.empty((w.shape[1], w.shape[0]), dtype=w.dtype, device=w.device)
+    with torch.cuda.device(w.device):
+        check(lib().ia_transpose16(w.data_ptr(), w.shape[0], w.shape[1], w.shape[1], wt.data_ptr(), wt.shape[1], _stream()))
+    return wt
+
+
+def project_dgrad_raw(d1, d2, wt, p, seed, step):
+    """df1, df2 = (d_pre @ w) * input-dropout mask / (1 - p): the forward GEMM kernel on (d_pre, w.T) with the mask in its epilogue."""
+    n, h = d1.shape
+    k = wt.shape[0]
+    df1 = torch.empty((n, k), dtype=d1.dtype, device=d1.device)
+    df2 = torch.empty((n, k), dtype=d1.dtype, device=d1.device)
+    with torch.cuda.device(d1.device):
+        check(lib().ia_project_dgrad(_DT[d1.dtype], d1.data_ptr(), d2.data_ptr(), _ld(d1), _ld(d2), n, h, wt.data_ptr(), _ld(wt), k,
+                                     df1.data_ptr(), df2.data_ptr(), k, k, float(p), int(seed), int(step), _stream()))
+    return df1, df2
+
+
+def project_wgrad_raw(d1, d2, f1d, f2d, want_db=True):
+    """dw [h, k] fp32 = d1.T @ f1d + d2.T @ f2d, db [h] fp32 = column sums of d1, d2: one tcgen05 GEMM contracting over the rows."""
+    n, h = d1.shape
+    k = f1d.shape[1]
+    dev = d1.device
+    d1, d2, f1d, f2d = (t if (t.stride(1) == 1 and t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0) else t.contiguous() for t in (d1, d2, f1d, f2d))
+    if _ld(d1) != _ld(d2):
+        d2 = d2.contiguous(); d1 = d1.contiguous()
+    if _ld(f1d) != _ld(f2d):
+        f1d = f1d.contiguous(); f2d = f2d.contiguous()
+    dw = torch.empty((h, k), dtype=torch.float32, device=dev)
+    db = torch.empty(h, dtype=torch.float32, device=dev) if want_db else None
+    with torch.cuda.device(dev):
+        need = lib().ia_project_wgrad_workspace_bytes(n, h, k)
+        ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+        off = (-ws.data_ptr()) % 256
+        check(lib().ia_project_wgrad(_DT[d1.dtype], d1.data_ptr(), d2.data_ptr(), _ld(d1), f1d.data_ptr(), f2d.data_ptr(), _ld(f1d), n, h, k,
+                                     dw.data_ptr(), db.data_ptr() if want_db else None, ws.data_ptr() + off, need, _stream()))
+    return dw, db
+
+
+def _project_backward(ctx_f1d, ctx_f2d, w16, d1, d2, p, seed, step, needs):
+    """Shared tail of the projection backward: data gradient (dgrad) and weight / bias gradients (wgrad) on the tensor cores."""
+    df1 = df2 = dw = db = None
+    if needs[0] or needs[1]:
+        df1, df2 = project_dgrad_raw(d1, d2, transpose16_raw(w16), p, seed, step)
+    if needs[2] or needs[3]:
+        dw, db = project_wgrad_raw(d1, d2, ctx_f1d, ctx_f2d, want_db=needs[3])
+    return df1, df2, dw, db
+
+
+class _ProjectTrainFn(torch.autograd.Function):
+    """(x, y) = drop(tanh(dense(drop(f1)))), drop(tanh(dense(drop(f2)))) -- VecSimClassificationHead.forward in train() mode
+    (reference base.py:50-53,67-75) -- with every GEMM of forward AND backward on tcgen05 kernels: forward GEMM with bias + tanh +
+    output dropout in its epilogue, data gradient through the same kernel on (d_pre, W^T) with the input mask in its epilogue,
+    weight gradient through the MN-major split-K GEMM.  Dropout masks are counter-based (seed, step): nothing is stored."""
+
+    @staticmethod
+    def forward(ctx, f1, f2, w, b, p, seed, step):
+        w16 = w.detach().to(f1.dtype)
+        f1d = dropout_raw(f1, p, seed, step, 0) if p > 0 else f1
+        f2d = dropout_raw(f2, p, seed, step, 1) if p > 0 else f2
+        x, y = project_tanh_dropout_raw(f1d, f2d, w16, b, p, seed, step)
+        ctx.save_for_backward(f1d, f2d, w16, x, y)
+        ctx.cfg = (float(p), int(seed), int(step), w.dtype, b.dtype if b is not None else None)
+        return x, y
+
+    @staticmethod
+    def backward(ctx, gx, gy):
+        f1d, f2d, w16, x, y = ctx.saved_tensors
+        p, seed, step, wdt, bdt = ctx.cfg
+        d1 = tanh_dropout_bwd_raw(gx if gx is not None else torch.zeros_like(x), x, p)
+        d2 = tanh_dropout_bwd_raw(gy if gy is not None else torch.zeros_like(y), y, p)
+        needs = (ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2], bdt is not None and ctx.needs_input_grad[3])
+        df1, df2, dw, db = _project_backward(f1d, f2d, w16, d1, d2, p, seed, step, needs)
+        return (df1 if needs[0] else None, df2 if needs[1] else None, dw.to(wdt) if needs[2] else None,
+                db.to(bdt) if needs[3] else None, None, None, None)
+
+
+class _ProjectScoreLossTrainFn(torch.autograd.Function):
+    """Head projection (train mode) + pair score + loss ladder + their whole backward: after the forward GEMM the fused pair-loss
+    launch writes d_pre (the gradient at the dense layer's output: loss backward, similarity backward, dropout and tanh backward in
+    one HBM pass, ia_pair_score_loss_act_bwd); backward() only runs the two gradient GEMMs.  An upstream scalar != 1 (GradScaler,
+    gradient accumulation) re-issues the pair launch with the scalar folded in before the rounding, like _FusedPairLossFn."""
+
+    @staticmethod
+    def forward(ctx, f1, f2, w, b, labels, measure, loss_type, margin, p, seed, step):
+        w16 = w.detach().to(f1.dtype)
+        f1d = dropout_raw(f1, p, seed, step, 0) if p > 0 else f1
+        f2d = dropout_raw(f2, p, seed, step, 1) if p > 0 else f2
+        x, y = project_tanh_dropout_raw(f1d, f2d, w16, b, p, seed, step)
+        n, h = x.shape
+        labels = _labels_i64(labels, n)
+        sim = torch.empty(n, dtype=torch.float32, device=x.device)
+        probs = torch.empty(n, dtype=torch.float32, device=x.device)
+        loss = torch.empty(1, dtype=torch.float32, device=x.device)
+        d1 = torch.empty_like(x)
+        d2 = torch.empty_like(y)
+        with torch.cuda.device(x.device):
+            ws = workspace(x.device)
+            check(lib().ia_pair_score_loss_act_bwd(
+                _measure_id(measure), LOSSES[loss_type], float(margin), REDUCTIONS["mean"], _DT[x.dtype], _DT[x.dtype], x.data_ptr(), y.data_ptr(),
+                h, h, labels.data_ptr(), n, h, sim.data_ptr(), probs.data_ptr(), loss.data_ptr(), d1.data_ptr(), d2.data_ptr(), h, h, 1.0, None, 0,
+                _keep_scale(p), ws.data_ptr(), ws.numel(), _stream()))
+        ctx.save_for_backward(f1d, f2d, w16, x, y, labels)
+        ctx.first = (d1, d2)
+        ctx.cfg = (float(p), int(seed), int(step), w.dtype, b.dtype if b is not None else None, measure, loss_type, float(margin))
+        ctx.mark_non_differentiable(sim, probs)
+        ctx.set_materialize_grads(False)
+        return x, y, sim, probs, loss[0]
+
+    @staticmethod
+    def backward(ctx, gx, gy, _gs, _gp, gloss):
+        f1d, f2d, w16, x, y, labels = ctx.saved_tensors
+        p, seed, step, wdt, bdt, measure, loss_type, margin = ctx.cfg
+        n, h = x.shape
+        first, ctx.first = ctx.first, None
+        have = first is not None
+        d1, d2 = first if have else (torch.empty_like(x), torch.empty_like(y))
+        if gloss is None:
+            d1.zero_(); d2.zero_()
+        else:
+            up = gloss.detach().to(torch.float32).reshape(1).contiguous()
+            with torch.cuda.device(x.device):
+                ws = workspace(x.device)
+                check(lib().ia_pair_score_loss_act_bwd(
+                    _measure_id(measure), LOSSES[loss_type], margin, REDUCTIONS["mean"], _DT[x.dtype], _DT[x.dtype], x.data_ptr(), y.data_ptr(),
+                    h, h, labels.data_ptr(), n, h, None, None, None, d1.data_ptr(), d2.data_ptr(), h, h, 1.0, up.data_ptr(), int(have),
+                    _keep_scale(p), ws.data_ptr(), ws.numel(), _stream()))
+        if gx is not None:        # the embeddings were also used elsewhere: add that path's contribution
+            d1 = d1 + tanh_dropout_bwd_raw(gx, x, p)
+        if gy is not None:
+            d2 = d2 + tanh_dropout_bwd_raw(gy, y, p)
+        needs = (ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2], bdt is not None and ctx.needs_input_grad[3])
+        df1, df2, dw, db = _project_backward(f1d, f2d, w16, d1, d2, p, seed, step, needs)
+        return (df1 if needs[0] else None, df2 if needs[1] else None, dw.to(wdt) if needs[2] else None,
+                db.to(bdt) if needs[3] else None, None, None, None, None, None, None, None)
+
+
+def project_tanh_train(f1, f2, w, b, p, seed, step):
+    """Training-mode projection of both sides (dropout p on the features and on the tanh outputs), differentiable."""
+    f1, f2, _, _ = _prep_project(f1, f2, w, b)
+    return _ProjectTrainFn.apply(f1, f2, w, b, float(p), int(seed), int(step))
+
+
+def project_score_loss_train(measure, loss_type, f1, f2, w, b, labels, p, seed, step, margin=1.0):
+    """(x, y, sim, probs, loss) of the training step from the encoder features: projection with dropout, pair score, loss ladder;
+    loss.backward() runs the fused gradient launch's d_pre through the two gradient GEMMs."""
+    if loss_type not in LOSSES:
+        raise ValueError(f"unsupported loss_type for a vector-similarity head: {loss_type}")
+    f1, f2, _, _ = _prep_project(f1, f2, w, b)
+    return _ProjectScoreLossTrainFn.apply(f1, f2, w, b, labels, measure, loss_type, float(margin), float(p), int(seed), int(step))
+
+
 # ------------------------------------------------------------------------------------------- autograd
 class _PairScoreFn(torch.autograd.Function):
     """sim = similarity(x, y) with the backward kernel (unfused head -> loss module sequence of the reference)."""
@@ -514,32 +711,6 @@ class _FusedSoftmaxCEFn(torch.autograd.Function):
         return dx, dy, dw.to(ctx.wdtype), db.to(ctx.bdtype), None
 
 
-class _ProjectTanhFn(torch.autograd.Function):
-    """(x, y) = tanh(dense(f1)), tanh(dense(f2)) on the fused GEMM; the backward is plain library GEMMs
-    (d_pre = g * (1 - out^2); dW = d_pre^T f, db = sum d_pre, df = d_pre W), SURVEY 8 row a6."""
-
-    @staticmethod
-    def forward(ctx, f1, f2, w, b):
-        x, y = project_tanh_raw(f1, f2, w, b)
-        ctx.save_for_backward(f1, f2, w, x, y)
-        ctx.has_bias = b is not None
-        ctx.bdtype = b.dtype if b is not None else None
-        return x, y
-
-    @staticmethod
-    def backward(ctx, gx, gy):
-        f1, f2, w, x, y = ctx.saved_tensors
-        cd = x.dtype
-        p1 = (gx.float() * (1.0 - x.float() ** 2)).to(cd)
-        p2 = (gy.float() * (1.0 - y.float() ** 2)).to(cd)
-        wc = w.to(cd)
-        df1 = (p1 @ wc).to(f1.dtype) if ctx.needs_input_grad[0] else None
-        df2 = (p2 @ wc).to(f2.dtype) if ctx.needs_input_grad[1] else None
-        dw = (p1.t() @ f1.to(cd) + p2.t() @ f2.to(cd)).to(w.dtype) if ctx.needs_input_grad[2] else None
-        db = (p1.float().sum(0) + p2.float().sum(0)).to(ctx.bdtype) if (ctx.has_bias and ctx.needs_input_grad[3]) else None
-        return df1, df2, dw, db
-
-
 # ------------------------------------------------------------------------------------------- public
 def pair_similarity(measure, x, y):
     """similarity(x, y) -> [N] fp32, differentiable (reference base.py:54-62,77)."""
@@ -611,7 +782,7 @@ def softmax_head_ce(x, y, w, b, labels):
 def project_tanh(f1, f2, w, b):
     """(x, y) = tanh(linear(f1, w, b)), tanh(linear(f2, w, b)), differentiable (reference base.py:67-75, eval mode)."""
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (f1, f2, w, b)):
-        return _ProjectTanhFn.apply(f1, f2, w, b)
+        return project_tanh_train(f1, f2, w, b, 0.0, 0, 0)       # p = 0: same forward kernel, backward on the gradient GEMMs
     return project_tanh_raw(f1, f2, w, b)
 
 

@@ -5,9 +5,9 @@ src/models/base.py, with the similarity / probability / loss arithmetic on the s
     TwoTowerClassificationHead(h, dropout, num_labels)     -> (x, y, logits, probs)   base.py:96-117
     InnerProduct(normalize=False).forward(x1, x2)          -> [N]                     base.py:25-34
 
-The dense -> tanh projection of the VecSim head runs as one tcgen05 GEMM with bias + tanh in its epilogue
-(csrc/projection.cu) for bf16 / fp16 features when dropout is inactive, and on cuBLAS/ATen otherwise (SURVEY 8
-row a6: boundary-adjacent).
+The dense -> tanh projection of the VecSim head runs as one tcgen05 GEMM with bias + tanh (+ dropout in train() mode) in its
+epilogue (csrc/projection.cu) for bf16 / fp16 features, its backward as two more tcgen05 GEMMs (csrc/projection_bwd.cu); fp32
+features stay on cuBLAS/ATen (boundary-adjacent).
 `forward_with_loss` is the fused single-pass entry the reference's forward() can call instead of
 classifier(...) + the loss ladder.
 """
@@ -80,10 +80,8 @@ class VecSimClassificationHead(nn.Module):
         return self.dropout(x)
 
     def _fused_dtype(self, f1, f2):
-        """dtype the fused tcgen05 projection would run in, or None when the library path must be used: dropout
-        active (torch's RNG stream cannot be reproduced inside the GEMM), fp32 arithmetic, or odd shapes."""
-        if self.training and self.dropout.p > 0:
-            return None
+        """dtype the fused tcgen05 projection would run in, or None when the library path must be used: fp32 arithmetic
+        (TF32 tensor cores would change the numerics) or odd shapes."""
         if not (f1.is_cuda and f2.is_cuda) or f1.dim() != 2 or f1.shape != f2.shape:
             return None
         dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else f1.dtype
@@ -94,11 +92,24 @@ class VecSimClassificationHead(nn.Module):
         k, h = self.dense.in_features, self.dense.out_features
         return dt if (f1.shape[1] == k and k % 8 == 0 and h % 8 == 0 and h <= 4096) else None
 
+    def _dropout_state(self):
+        """(p, seed, step) of this call's dropout masks: counter-based (csrc/philox.cuh), seeded from torch's global seed, one
+        step per call -- reproducible under torch.manual_seed, no host synchronisation.  p = 0 outside train()."""
+        p = float(self.dropout.p) if self.training else 0.0
+        if p <= 0.0:
+            return 0.0, 0, 0
+        self._dropout_step = getattr(self, "_dropout_step", 0) + 1
+        return p, torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, self._dropout_step & 0xFFFFFFFF
+
     def project_pair(self, features_1, features_2):
-        """Both sides through dense -> tanh: one fused GEMM launch when possible."""
+        """Both sides through dropout -> dense -> tanh -> dropout: fused GEMM launches when possible, forward
+        and backward (train() mode included: the dropout masks are generated inside the kernels)."""
         dt = self._fused_dtype(features_1, features_2)
         if dt is None:
             return self.project(features_1), self.project(features_2)
+        p, seed, step = self._dropout_state()
+        if p > 0.0:
+            return F_.project_tanh_train(features_1.to(dt), features_2.to(dt), self.dense.weight, self.dense.bias, p, seed, step)
         return F_.project_tanh(features_1.to(dt), features_2.to(dt), self.dense.weight, self.dense.bias)
 
     def forward(self, features_1, features_2):
@@ -108,7 +119,7 @@ class VecSimClassificationHead(nn.Module):
         dt = self._fused_dtype(features_1, features_2)
         needs_grad = torch.is_grad_enabled() and (
             features_1.requires_grad or features_2.requires_grad or self.dense.weight.requires_grad)
-        if dt is not None and not needs_grad:
+        if dt is not None and not needs_grad and not (self.training and self.dropout.p > 0):
             # inference: projection, score and probability map in one launch
             return F_.project_score(measure, features_1.to(dt), features_2.to(dt), self.dense.weight, self.dense.bias,
                                     want_embeds=True)
@@ -117,8 +128,15 @@ class VecSimClassificationHead(nn.Module):
         return x, y, sim, probs
 
     def forward_with_loss(self, features_1, features_2, labels, loss_type, margin=1.0):
-        """Head + loss ladder (reference text.py:1468-1477) + their backward in one HBM pass.
-        Returns (x, y, sim, probs, loss); loss.backward() continues into dense/tanh through autograd."""
+        """Head + loss ladder (reference text.py:1468-1477) + their backward.  16-bit features: forward GEMM (bias + tanh +
+        dropout epilogue), ONE pair launch that produces sim, probs, loss and d_pre (loss, similarity, dropout and tanh backward
+        folded together), and the two gradient GEMMs in backward() -- all on this library's kernels.  Otherwise the projection
+        stays on torch and the pair launch is fused as before.  Returns (x, y, sim, probs, loss)."""
+        dt = self._fused_dtype(features_1, features_2)
+        if dt is not None and torch.is_grad_enabled():
+            p, seed, step = self._dropout_state()
+            return F_.project_score_loss_train(self.config.similarity_measure, loss_type, features_1.to(dt), features_2.to(dt),
+                                               self.dense.weight, self.dense.bias, labels, p, seed, step, margin)
         x, y = self.project_pair(features_1, features_2)
         sim, probs, loss = F_.pair_score_loss(self.config.similarity_measure, loss_type, x, y, labels, margin)
         return x, y, sim, probs, loss

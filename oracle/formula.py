@@ -235,3 +235,33 @@ def best_f1_and_threshold(scores, labels, high_score_more_similar=True):
     fneg = nextract[best] - ncorrect[best]
     acc = (ncorrect[best] + neg_total - fneg) / n
     return float(acc), float(f1[best]), float(precision[best]), float(recall[best]), float((ss[best] + ss[best + 1]) / 2)
+
+
+# ---------------------------------------------------------------------------------------------- dropout mask replay
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 on numpy uint32 arrays (Salmon et al. 2011; the generator family of torch's CUDA dropout)."""
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), 0x9E3779B9, 0xBB67AE85
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint32) for c in (c0, c1, c2, c3))
+    k0, k1 = int(k0), int(k1)
+    for _ in range(10):
+        p0 = M0 * c0.astype(np.uint64)
+        p1 = M1 * c2.astype(np.uint64)
+        hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), p0.astype(np.uint32)
+        hi1, lo1 = (p1 >> np.uint64(32)).astype(np.uint32), p1.astype(np.uint32)
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint32(k0), lo1, hi0 ^ c3 ^ np.uint32(k1), lo0
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def philox_keep_mask(rows, cols, p, seed, step, stream):
+    """The keep mask csrc/philox.cuh defines for a [rows, cols] tensor: element (row, col) = 16-bit lane (row & 7) of
+    philox4x32_10(counter = (g_lo, g_hi, stream, step), key = seed), g = (row >> 3) * cols + col; kept <=> lane >= round(p * 2^16).
+    Test infrastructure: replays the masks of ia_dropout_fwd / ia_project_tanh_fwd(dropout) on the host."""
+    thr = min(65535, max(0, int(np.float32(p) * np.float32(65536.0) + np.float32(0.5))))
+    groups = (rows + 7) // 8
+    g = (np.arange(groups, dtype=np.uint64)[:, None] * np.uint64(cols) + np.arange(cols, dtype=np.uint64)[None, :])
+    r = philox4x32_10((g & np.uint64(0xFFFFFFFF)).astype(np.uint32), (g >> np.uint64(32)).astype(np.uint32),
+                      np.full(g.shape, stream, np.uint32), np.full(g.shape, step, np.uint32), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    lanes = np.stack([r[0] & 0xFFFF, r[0] >> 16, r[1] & 0xFFFF, r[1] >> 16, r[2] & 0xFFFF, r[2] >> 16, r[3] & 0xFFFF, r[3] >> 16], axis=1)
+    keep = lanes >= thr                                  # [groups, 8, cols]
+    return keep.reshape(groups * 8, cols)[:rows]

@@ -152,7 +152,7 @@ def test_head_module_uses_fused_projection():
     check_embeddings(x, rx, torch.bfloat16, "x", acc_noise(f1, head.dense.weight.cpu(), head.dense.bias.float().cpu()))
     ox, oy = x.float().cpu(), y.float().cpu()
     parity.assert_scores_close("cosine", sim, torch_port.similarity("cosine", ox, oy), ox, oy, 1e-5)
-    # training mode with dropout active goes through the library path (torch RNG), still on the GPU
+    # training mode with dropout active: the fused kernels generate the masks (test_head_train_step_fused_vs_oracle_graph)
     head.train()
     x2, y2, sim2, _ = head(f1.to(DEV), f2.to(DEV))
     assert x2.requires_grad and sim2.requires_grad
@@ -207,3 +207,120 @@ def test_project_rejects_what_it_cannot_do():
         F_.project_tanh_raw(fb[:, :60].contiguous(), fb[:, :60].contiguous(), wb[:, :60].contiguous(), None)   # K % 8 != 0
     with pytest.raises(RuntimeError):
         F_.project_tanh_raw(fb.cpu(), fb.cpu(), wb.cpu(), None)
+
+
+# ----------------------------------------------------------------------------------------------- round 2: training side
+def _oracle_train_graph(f1, f2, w, b, p, seed, step, want="xy"):
+    """VecSimClassificationHead.forward in train() mode (reference base.py:67-75) with the masks of csrc/philox.cuh replayed on
+    the host: x = drop(tanh(dense(drop(f)))).  fp32 torch graph on the 16-bit-quantised leaves."""
+    from oracle import formula
+    n, k = f1.shape
+    h = w.shape[0]
+    s = 1.0 / (1.0 - p) if p > 0 else 1.0
+    leaves = [t.float().clone().requires_grad_(True) for t in (f1, f2, w, b)]
+    outs, masks = [], []
+    for side, f in enumerate(leaves[:2]):
+        m_in = torch.from_numpy(formula.philox_keep_mask(n, k, p, seed, step, side)) if p > 0 else torch.ones(n, k, dtype=torch.bool)
+        m_out = torch.from_numpy(formula.philox_keep_mask(n, h, p, seed, step, 2 + side)) if p > 0 else torch.ones(n, h, dtype=torch.bool)
+        if p > 0:      # the kernel rounds the dropped features once: rounded value, straight-through gradient
+            fd = (f * m_in * s).detach().to(f1.dtype).float() + (f * m_in * s - (f * m_in * s).detach())
+        else:
+            fd = f
+        t = torch.tanh(torch.nn.functional.linear(fd, leaves[2], leaves[3]))
+        outs.append(t * m_out * s)
+        masks.append((m_in, m_out))
+    return leaves, outs, masks
+
+
+def test_dropout_masks_replay_and_rate():
+    """ia_dropout_fwd against the host replay of the Philox masks (exact), and the keep rate."""
+    import item_alignment_b200.functional as F_
+    from oracle import formula
+    gen = torch.Generator().manual_seed(2)
+    for dt, rows, cols, p in ((torch.bfloat16, 1003, 264, 0.1), (torch.float16, 64, 1024, 0.5), (torch.bfloat16, 7, 8, 0.25)):
+        x = torch.randn(rows, cols, generator=gen).to(dt)
+        for stream_id, step in ((0, 1), (1, 7)):
+            out = F_.dropout_raw(x.to(DEV), p, 1234567890123, step, stream_id).cpu()
+            keep = torch.from_numpy(formula.philox_keep_mask(rows, cols, p, 1234567890123, step, stream_id))
+            ref = torch.where(keep, (x.float() * (1.0 / (1.0 - p))).to(dt), torch.zeros((), dtype=dt))
+            assert torch.equal(out, ref), (dt, rows, cols, p, stream_id)
+    big = F_.dropout_raw(torch.ones(8192, 1024, dtype=torch.bfloat16, device=DEV), 0.1, 99, 3, 0)
+    rate = float((big != 0).float().mean())
+    assert abs(rate - 0.9) < 3 * (0.09 / 8192 / 1024) ** 0.5 + 2e-5, rate          # binomial 3 sigma + the 2^-16 quantisation of p
+    assert abs(float(big.float().mean()) - 1.0) < 2e-3                                # unbiased up to bf16(1/0.9)
+    assert not torch.equal(big, F_.dropout_raw(torch.ones(8192, 1024, dtype=torch.bfloat16, device=DEV), 0.1, 99, 4, 0))   # next step: new mask
+
+
+@pytest.mark.parametrize("n,k,h,dt,p", [(300, 256, 128, torch.bfloat16, 0.1), (300, 264, 136, torch.bfloat16, 0.0),
+                                        (300, 264, 136, torch.bfloat16, 0.1), (1000, 1024, 1024, torch.bfloat16, 0.1),
+                                        (129, 768, 768, torch.float16, 0.3), (64, 64, 64, torch.bfloat16, 0.0)])
+def test_project_train_forward_and_backward_vs_oracle_graph(n, k, h, dt, p):
+    """Training-mode projection: forward (input dropout kernel, GEMM with bias + tanh + output dropout epilogue) and backward
+    (tanh / dropout backward, data-gradient GEMM with the input mask in its epilogue, MN-major split-K weight-gradient GEMM,
+    bias gradient) against the fp32 autograd graph of the reference's ops with the same masks."""
+    import item_alignment_b200.functional as F_
+    f1, f2, w, b = make_case(n, k, h, dt, seed=n + h)
+    seed, step = 424242, 5
+    gen = torch.Generator().manual_seed(n)
+    gx, gy = torch.randn(n, h, generator=gen).to(dt), torch.randn(n, h, generator=gen).to(dt)
+    a = [t.to(DEV).requires_grad_(True) for t in (f1, f2, w, b)]
+    x, y = F_.project_tanh_train(a[0], a[1], a[2], a[3], p, seed, step)
+    leaves, (rx, ry), masks = _oracle_train_graph(f1, f2, w, b, p, seed, step)
+    for ours, ref, (m_in, m_out), name in ((x, rx, masks[0], "x"), (y, ry, masks[1], "y")):
+        o = ours.float().cpu()
+        assert bool(((o == 0) | m_out).all()), f"{name}: a dropped element is not zero"
+        check_embeddings(ours, ref.detach(), dt, name, acc_noise(f1, w, b) * (1.0 / (1.0 - p)) ** 2 * 2)
+    torch.autograd.backward([x, y], [gx.to(DEV), gy.to(DEV)])
+    torch.autograd.backward([rx, ry], [gx.float(), gy.float()])
+    bad = []
+    for ours, ref, name in zip(a, leaves, ("df1", "df2", "dw", "db")):
+        scale = float(ref.grad.abs().max())
+        err = float((ours.grad.float().cpu() - ref.grad).abs().max())
+        if not err <= 3e-2 * scale:                                          # 16-bit d_pre / operands, fp32 accumulation
+            bad.append(f"{name}: {err:.4g} vs scale {scale:.4g}")
+    assert not bad, "; ".join(bad)
+    if p > 0:       # the data gradient is exactly zero where the input was dropped
+        assert bool(((a[0].grad.cpu() == 0) | masks[0][0]).all()) and bool(((a[1].grad.cpu() == 0) | masks[1][0]).all())
+
+
+def test_head_train_step_fused_vs_oracle_graph():
+    """two_tower_step in train() mode with dropout 0.1: projection + pair loss + the whole backward on this library's kernels,
+    against the reference's ops with replayed masks; GradScaler-style upstream scale and second backward included."""
+    import types
+    import item_alignment_b200 as ia
+    from oracle import torch_port
+    cfg = types.SimpleNamespace(cls_layers="12", cls_pool="cls", hidden_size=256, classifier_dropout=None, hidden_dropout_prob=0.1,
+                                similarity_measure="cosine", loss_type="bce", loss_margin=1.0)
+    torch.manual_seed(77)
+    head = ia.VecSimClassificationHead(cfg).to(DEV).bfloat16().train()
+    gen = torch.Generator().manual_seed(3)
+    n = 515
+    f1 = torch.randn(n, 256, generator=gen).to(torch.bfloat16)
+    f2 = torch.randn(n, 256, generator=gen).to(torch.bfloat16)
+    labels = (torch.rand(n, generator=gen) < 0.5).long()
+    a1, a2 = f1.to(DEV).requires_grad_(True), f2.to(DEV).requires_grad_(True)
+    before = ia.launch_count()
+    out = ia.two_tower_step(head, cfg, a1, a2, labels.to(DEV))
+    (out["loss"] * 8.0).backward(retain_graph=True)
+    launched = ia.launch_count() - before
+    step = head._dropout_step
+    w, b = head.dense.weight.detach().cpu(), head.dense.bias.detach().float().cpu()
+    leaves, (rx, ry), masks = _oracle_train_graph(f1, f2, w, b, 0.1, torch.initial_seed(), step)
+    rsim = torch_port.similarity("cosine", rx, ry)
+    rloss = torch_port.loss_ladder("bce", rsim, rx, ry, labels)
+    (rloss * 8.0).backward()
+    assert abs(float(out["loss"]) - float(rloss)) <= 2e-2 * abs(float(rloss))
+    for ours, ref, name in ((a1.grad, leaves[0].grad, "df1"), (a2.grad, leaves[1].grad, "df2"), (head.dense.weight.grad, leaves[2].grad, "dw"),
+                            (head.dense.bias.grad, leaves[3].grad, "db")):
+        scale = float(ref.abs().max())
+        err = float((ours.float().cpu() - ref).abs().max())
+        assert err <= 5e-2 * scale, f"{name}: {err} vs scale {scale}"
+    g1 = a1.grad.clone()
+    (out["loss"] * 8.0).backward()                  # second backward through the same node: gradients double, nothing scaled twice
+    torch.testing.assert_close(a1.grad.float(), 2 * g1.float(), rtol=2e-2, atol=2e-2 * float(g1.abs().max()))
+    assert launched >= 7        # dropout x2, GEMM, pair launch (+ its no-op re-issue), transpose, dgrad, wgrad + reduce + column sums
+    # eval mode: no dropout, inference path untouched
+    head.eval()
+    with torch.no_grad():
+        xe, ye, _, _ = head(f1.to(DEV), f2.to(DEV))
+    assert float((xe == 0).float().mean()) < 0.01
