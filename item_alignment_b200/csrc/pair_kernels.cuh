@@ -119,7 +119,9 @@ constexpr int kBulkStages = 3;
 
 // ROWS: pairs a warp processes per iteration (their loads are all issued up front).  2 KB rows (16-bit, D=1024)
 // use ROWS=2 so that a warp has 8 KB in flight per iteration like a 4 KB fp32 row does.
-template <typename T, typename G, int MEASURE, int MODE, bool COSLOSS, int VPL, bool BULK, int ROWS>
+// ACT: the backward of the head's tanh (+ dropout) is folded into the gradient store (PairParams::act_bwd).  A template
+// parameter, not a run-time test: the test alone cost the benchmarked instantiation 2 % (93.4 vs 91.3 us at config 2).
+template <typename T, typename G, int MEASURE, int MODE, bool COSLOSS, int VPL, bool BULK, int ROWS, bool ACT = false>
 __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
   static_assert(!BULK || ROWS == 1, "the bulk ring feeds one row per iteration");
   constexpr int E = VecTraits<T>::kElems;
@@ -308,20 +310,25 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
             unpack<T>(yv[k][i], fy);
 #pragma unroll
             for (int j = 0; j < E; ++j) {
-              if (kGradCosForm) {
-                gx[j] = c.A * fy[j] - c.Bx * fx[j];
-                gy[j] = c.A * fx[j] - c.By * fy[j];
+              if (MEASURE == IA_INNER && !COSLOSS) {
+                gx[j] = __fmul_rn(c.A, fy[j]);          // Bx = By = 0
+                gy[j] = __fmul_rn(c.A, fx[j]);
+              } else if (kGradCosForm) {
+                // explicit rounding points: every instantiation of this kernel (ROWS = 1 / 2, gathered, generic) must produce
+                // the same bits, whatever the compiler would choose to contract
+                gx[j] = __fmaf_rn(c.A, fy[j], -__fmul_rn(c.Bx, fx[j]));
+                gy[j] = __fmaf_rn(c.A, fx[j], -__fmul_rn(c.By, fy[j]));
               } else if (MEASURE == IA_L1) {
                 const float dd = fx[j] - fy[j] + kPdistEps;
                 gx[j] = dd > 0.f ? c.A : (dd < 0.f ? -c.A : 0.f);
                 gy[j] = -gx[j];
               } else {
-                const float dd = fx[j] - fy[j] + kPdistEps;
-                gx[j] = c.A * dd;
+                const float dd = __fadd_rn(__fsub_rn(fx[j], fy[j]), kPdistEps);
+                gx[j] = __fmul_rn(c.A, dd);
                 gy[j] = -gx[j];
               }
             }
-            if (p.act_bwd > 0.f) {
+            if (ACT) {
               // tanh (and dropout) backward fused into the store: t = out / scale where kept; with dropout active a dropped
               // element is recognised by its exact zero (a kept tanh value is 0 only for a pre-activation of exactly 0)
               const float sc = p.act_bwd, inv = 1.0f / p.act_bwd;
@@ -329,8 +336,8 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
 #pragma unroll
               for (int j = 0; j < E; ++j) {
                 const float tx = fx[j] * inv, ty = fy[j] * inv;
-                gx[j] = (drop && fx[j] == 0.f) ? 0.f : gx[j] * sc * (1.0f - tx * tx);
-                gy[j] = (drop && fy[j] == 0.f) ? 0.f : gy[j] * sc * (1.0f - ty * ty);
+                gx[j] = (drop && fx[j] == 0.f) ? 0.f : __fmul_rn(__fmul_rn(gx[j], sc), __fmaf_rn(-tx, tx, 1.0f));
+                gy[j] = (drop && fy[j] == 0.f) ? 0.f : __fmul_rn(__fmul_rn(gy[j], sc), __fmaf_rn(-ty, ty, 1.0f));
               }
             }
             Packer<G, E>::store(dxr + (int64_t)v * E, gx);
@@ -356,7 +363,7 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
 }
 
 // Any D, any alignment: scalar loads, two sweeps over the row (the second one hits L1/L2).
-template <typename T, typename G, int MEASURE, int MODE, bool COSLOSS>
+template <typename T, typename G, int MEASURE, int MODE, bool COSLOSS, bool ACT = false>
 __global__ void __launch_bounds__(256) pair_kernel_generic(const PairParams p) {
   constexpr bool kGradCosForm = COSLOSS || MEASURE == IA_INNER || MEASURE == IA_COSINE;
   const int lane = threadIdx.x & 31;
@@ -425,23 +432,26 @@ __global__ void __launch_bounds__(256) pair_kernel_generic(const PairParams p) {
       for (int j = lane; j < p.d; j += 32) {
         const float fx = to_float<T>(xr[j]), fy = to_float<T>(yr[j]);
         float gx, gy;
-        if (kGradCosForm) {
-          gx = c.A * fy - c.Bx * fx;
-          gy = c.A * fx - c.By * fy;
+        if (MEASURE == IA_INNER && !COSLOSS) {
+          gx = __fmul_rn(c.A, fy);
+          gy = __fmul_rn(c.A, fx);
+        } else if (kGradCosForm) {
+          gx = __fmaf_rn(c.A, fy, -__fmul_rn(c.Bx, fx));
+          gy = __fmaf_rn(c.A, fx, -__fmul_rn(c.By, fy));
         } else if (MEASURE == IA_L1) {
           const float dd = fx - fy + kPdistEps;
           gx = dd > 0.f ? c.A : (dd < 0.f ? -c.A : 0.f);
           gy = -gx;
         } else {
-          gx = c.A * (fx - fy + kPdistEps);
+          gx = __fmul_rn(c.A, __fadd_rn(__fsub_rn(fx, fy), kPdistEps));
           gy = -gx;
         }
-        if (p.act_bwd > 0.f) {
+        if (ACT) {
           const float sc = p.act_bwd, inv = 1.0f / p.act_bwd;
           const bool drop = p.act_bwd != 1.0f;
           const float tx = fx * inv, ty = fy * inv;
-          gx = (drop && fx == 0.f) ? 0.f : gx * sc * (1.0f - tx * tx);
-          gy = (drop && fy == 0.f) ? 0.f : gy * sc * (1.0f - ty * ty);
+          gx = (drop && fx == 0.f) ? 0.f : __fmul_rn(__fmul_rn(gx, sc), __fmaf_rn(-tx, tx, 1.0f));
+          gy = (drop && fy == 0.f) ? 0.f : __fmul_rn(__fmul_rn(gy, sc), __fmaf_rn(-ty, ty, 1.0f));
         }
         dxr[j] = from_float<G>(gx);
         dyr[j] = from_float<G>(gy);
@@ -520,10 +530,33 @@ inline int pair_rows_pref() {
   return v;
 }
 
+// activation-backward variants exist for the fused mode of 16-bit tensors with gradients in the same type (what the head's
+// training path produces); anything else is refused loudly
+template <typename T, typename G, int MEASURE, int MODE, bool COSLOSS>
+int launch_pair_act(const PairParams& p, bool vec_ok, cudaStream_t stream) {
+  if constexpr (MODE == kModeFused && sizeof(T) == 2 && sizeof(G) == 2) {
+    constexpr int E = VecTraits<T>::kElems;
+    const int nvec = p.d / E;
+    if (!vec_ok || nvec > 32 * 8) return launch_rows<pair_kernel_generic<T, G, MEASURE, MODE, COSLOSS, true>>(p, stream);
+    const size_t row_bytes = (size_t)p.d * sizeof(T);
+    const bool group = pair_rows_pref() > 1 && p.n >= 16384 && row_bytes >= 1536 && row_bytes <= 3072;
+    if (nvec <= 64) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 2, false, 1, true>>(p, stream);
+    if (nvec <= 128) {
+      if (group) return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, false, 2, true>>(p, stream);
+      return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 4, false, 1, true>>(p, stream);
+    }
+    return launch_rows<pair_kernel<T, G, MEASURE, MODE, COSLOSS, 8, false, 1, true>>(p, stream);
+  } else {
+    set_error("activation backward (act_bwd_scale > 0) is offered for the fused launch on bf16 / fp16 tensors with gradients in the same type");
+    return IA_ERR_UNSUPPORTED;
+  }
+}
+
 template <typename T, typename G, int MEASURE, int MODE, bool COSLOSS>
 int launch_pair_vpl(const PairParams& p, bool vec_ok, cudaStream_t stream) {
   constexpr int E = VecTraits<T>::kElems;
   const int nvec = p.d / E;
+  if (p.act_bwd > 0.f) return launch_pair_act<T, G, MEASURE, MODE, COSLOSS>(p, vec_ok, stream);
   if (!vec_ok || nvec > 32 * 8) return launch_rows<pair_kernel_generic<T, G, MEASURE, MODE, COSLOSS>>(p, stream);
   // big rows (>= 1 KB) of the forward / fused kernels go through the bulk-copy ring
   if (MODE != kModeBwd && pair_bulk_enabled() && (size_t)p.d * sizeof(T) >= 1024 && p.n >= 1024 && p.xi == nullptr) {

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) tanh_dropout_bwd_kernel(const T* __restri
     for (int j = 0; j < 8; ++j) {
       const float o = h2f<T>(oe[j]), t = o * inv;
       const bool keep = keep_scale > 0.f ? (o != 0.f) : true;
-      re[j] = keep ? f2h<T>(h2f<T>(ge[j]) * sc * (1.0f - t * t)) : (unsigned short)0;
+      re[j] = keep ? f2h<T>(__fmul_rn(__fmul_rn(h2f<T>(ge[j]), sc), __fmaf_rn(-t, t, 1.0f))) : (unsigned short)0;
     }
     *reinterpret_cast<uint4*>(dpre + row * ldd + c0) = r;
   }
@@ -250,46 +250,49 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 }
 
 // db[c] = sum over the rows of d1 and d2 of column c.  Stage 1: a CTA takes 256 rows; warp w accumulates rows w, w+8, ... in
-// registers (a lane owns column pairs 2*lane + 64*j: every warp load is 128 contiguous bytes, all loads independent), the eight
-// warps are added in index order through shared memory.  Stage 2: one warp per column sums the CTA partials (lane-strided,
-// then a shuffle tree).  Fixed orders everywhere: deterministic.
-constexpr int kColsumRows = 256, kColsumMaxPairs = 16;    // up to 16 column pairs per lane: h <= 1024 per pass
+// registers (a lane owns 8 consecutive columns per 256-column group: 16-byte loads, a warp instruction reads 512 contiguous
+// bytes, all loads independent), the eight warps are added in index order through shared memory.  Stage 2: one warp per column
+// sums the CTA partials (lane-strided, then a shuffle tree).  Fixed orders everywhere: deterministic.
+constexpr int kColsumRows = 256, kColsumVecs = 4;    // 4 x 256 columns per pass
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ d1, const T* __restrict__ d2, int64_t ldd, int64_t rows, int cols,
                                                              float* __restrict__ partial) {
-  __shared__ float red[8][64];
+  __shared__ float red[8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t r0 = (int64_t)blockIdx.x * kColsumRows;
-  for (int cbase = 0; cbase < cols; cbase += 64 * kColsumMaxPairs) {
-    float a0[kColsumMaxPairs], a1[kColsumMaxPairs];
+  for (int cbase = 0; cbase < cols; cbase += 256 * kColsumVecs) {
+    float acc[kColsumVecs][8];
 #pragma unroll
-    for (int j = 0; j < kColsumMaxPairs; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+    for (int j = 0; j < kColsumVecs; ++j)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+#pragma unroll 2
     for (int rr = warp; rr < kColsumRows; rr += 8) {
       const int64_t r = r0 + rr;
       if (r >= 2 * rows) break;
       const T* src = r < rows ? d1 + r * ldd : d2 + (r - rows) * ldd;
 #pragma unroll
-      for (int j = 0; j < kColsumMaxPairs; ++j) {
-        const int c = cbase + 64 * j + 2 * lane;
+      for (int j = 0; j < kColsumVecs; ++j) {
+        const int c = cbase + 256 * j + 8 * lane;
         if (c < cols) {
-          const uint32_t v = *reinterpret_cast<const uint32_t*>(src + c);
-          a0[j] += h2f<T>((unsigned short)(v & 0xffffu));
-          a1[j] += h2f<T>((unsigned short)(v >> 16));
+          const uint4 v = ldg_stream(reinterpret_cast<const uint4*>(src + c));
+          const unsigned short* e16 = reinterpret_cast<const unsigned short*>(&v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[j][e] += h2f<T>(e16[e]);
         }
       }
     }
 #pragma unroll
-    for (int j = 0; j < kColsumMaxPairs; ++j) {
+    for (int j = 0; j < kColsumVecs; ++j) {
       __syncthreads();
-      red[warp][2 * lane] = a0[j]; red[warp][2 * lane + 1] = a1[j];
-      __syncthreads();
-      if (threadIdx.x < 64) {
-        float t = 0.f;
 #pragma unroll
-        for (int w2 = 0; w2 < 8; ++w2) t += red[w2][threadIdx.x];
-        const int c = cbase + 64 * j + threadIdx.x;
-        if (c < cols) partial[(size_t)blockIdx.x * cols + c] = t;
-      }
+      for (int e = 0; e < 8; ++e) red[warp][8 * lane + e] = acc[j][e];
+      __syncthreads();
+      float t = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < 8; ++w2) t += red[w2][threadIdx.x];
+      const int c = cbase + 256 * j + threadIdx.x;
+      if (c < cols) partial[(size_t)blockIdx.x * cols + c] = t;
     }
   }
 }
