@@ -296,6 +296,10 @@ int ia_unpack_keys(const uint64_t* keys, int64_t count, int descending, float* s
  * (submit/similarity.py:27, pred_bert.py:47-52) for a whole batch. */
 int ia_pair_score_host(int measure, int dtype, const void* x, const void* y, int64_t n, int64_t d,
                        float* sim, float* probs, double threshold, uint8_t* labels_out, int device);
+/* Page-locked host buffers for these entry points (full PCIe speed, no driver staging).  write_combined = 1 for buffers the CPU
+ * only writes and the device reads (x, y, labels): DMA reads skip the CPU-cache snoop; never read such a buffer on the CPU. */
+int ia_host_alloc(void** ptr, size_t bytes, int write_combined);
+int ia_host_free(void* ptr);
 int ia_pair_score_loss_host(int measure, int loss, float margin, int reduction, int dtype,
                             const void* x, const void* y, const int64_t* labels, int64_t n, int64_t d,
                             float* loss_out, void* dx, void* dy, int device);

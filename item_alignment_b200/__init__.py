@@ -11,14 +11,14 @@ from .heads import InnerProduct, PairSimilarity, TwoTowerClassificationHead, Vec
 from .metrics import find_best_f1_and_threshold, threshold_sweep
 from .loss import EuclideanDistanceLoss, HingeLoss, apply_loss_ladder, build_loss_fct, two_tower_step
 from .catalog_file import CatalogFile, jsonl_to_catalog, write_catalog
-from .retrieval import (CatalogIndex, ShardedCatalogIndex, all_gather_keys, merge_keys, rank_entities, shard_bounds,
+from .retrieval import (CatalogIndex, ShardedCatalogIndex, all_gather_keys, all_to_all_keys, merge_keys, rank_entities, shard_bounds,
                         unpack_keys)
 from .similarity import compute, compute_many, configure
 
 __all__ = [
     "functional", "IAError", "launch_count", "InnerProduct", "PairSimilarity", "TwoTowerClassificationHead",
     "VecSimClassificationHead", "EuclideanDistanceLoss", "HingeLoss", "apply_loss_ladder", "build_loss_fct",
-    "two_tower_step", "CatalogIndex", "ShardedCatalogIndex", "all_gather_keys", "merge_keys", "shard_bounds", "unpack_keys",
+    "two_tower_step", "CatalogIndex", "ShardedCatalogIndex", "all_gather_keys", "all_to_all_keys", "merge_keys", "shard_bounds", "unpack_keys",
     "compute", "compute_many", "configure", "find_best_f1_and_threshold", "threshold_sweep", "CatalogFile", "jsonl_to_catalog",
     "write_catalog", "rank_entities",
 ]

@@ -90,6 +90,8 @@ SIGNATURES = {
                                               ctypes.POINTER(c_int64)]),
     "ia_topk_merge": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
     "ia_unpack_keys": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "ia_host_alloc": (c_int, [ctypes.POINTER(c_void_p), c_size_t, c_int]),
+    "ia_host_free": (c_int, [c_void_p]),
     "ia_pair_score_host": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_double,
                                    c_void_p, c_int]),
     "ia_pair_score_loss_host": (c_int, [c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64,

@@ -98,6 +98,18 @@ using namespace ia;
 
 extern "C" {
 
+// Page-locked host buffers for the host entry points.  write_combined = 1: for buffers the CPU only WRITES and the device
+// reads (inputs): the device's DMA reads do not snoop the CPU caches; reading such memory from the CPU is slow.
+int ia_host_alloc(void** ptr, size_t bytes, int write_combined) {
+  if (ptr == nullptr || bytes == 0) { set_error("bad arguments"); return IA_ERR_INVALID; }
+  IA_CUDA_CHECK(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)));
+  return IA_OK;
+}
+int ia_host_free(void* ptr) {
+  if (ptr != nullptr) IA_CUDA_CHECK(cudaFreeHost(ptr));
+  return IA_OK;
+}
+
 int ia_pair_score_host(int measure, int dtype, const void* x, const void* y, int64_t n, int64_t d, float* sim,
                        float* probs, double threshold, uint8_t* labels_out, int device) {
   if (device < 0 || device >= 16) { set_error("bad device %d", device); return IA_ERR_INVALID; }

@@ -1,9 +1,9 @@
 #!/bin/bash
-# round 2: 8-GPU session -- bench at N = 8 (the driver's command line), N = 1 on the same box for the scaling ratio
+# round 2: 8-GPU session -- exchange-strategy A/B for C4, then bench at N = 8 (the driver's command line) and N = 1 on the same box
 mkdir -p gpurun_out
-nvidia-smi topo -m 2>&1 | head -n 12 | cut -c1-160
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29544 scripts/bench_c4_sharded.py 2>&1 | grep "^N=" | tee gpurun_out/c4_sharded_ab_n8_r02.log
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29545 scripts/bench_c4_sharded.py 2>&1 | grep "^N=" | tee gpurun_out/c4_sharded_ab_n4_r02.log
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench_n8_r02.json 2> gpurun_out/bench_n8_r02.err; echo "bench N=8 rc $?"
-tail -c 1500 gpurun_out/bench_n8_r02.json; echo; grep -i "error\|Traceback" -A5 gpurun_out/bench_n8_r02.err | head -n 30
 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_n1_8gpubox_r02.json 2> gpurun_out/bench_n1_8gpubox_r02.err; echo "bench N=1 rc $?"
 python - <<'PY'
 import json

@@ -16,9 +16,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "item_alignment_b200", "libia_b200.so")
 OUT = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles", "r02")
 FAMILIES = {"retrieve_tc_kernel": "sass_retrieve_tc_kernel.txt", "project_kernel": "sass_project_kernel.txt",
-            "project_bwd": "sass_project_bwd_kernels.txt", "pair_kernel": None, "softmax_head_kernel": None}
-MNEMONICS = ("UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "STTM", "UTCBAR", "SYNCS", "UTCATOMSWS", "LDGSTS", "REDUX",
-             "LDG.E.128", "STG.E.128", "LDS.128", "MUFU", "HMMA", "IMAD", "FFMA")
+            "wgrad_kernel": "sass_wgrad_kernel.txt", "softmax_head_mma_kernel": "sass_softmax_head_mma_kernel.txt",
+            "radix_scatter_kernel": None, "pair_kernel": None, "softmax_head_kernel": None}
+MNEMONICS = ("UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "STTM", "UTCBAR", "SYNCS", "UTCATOMSWS", "LDGSTS", "LDSM", "HMMA",
+             "MATCH", "REDUX", "LDG.E.128", "STG.E.128", "LDS.128", "MUFU", "IMAD", "FFMA")
 
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
 funcs, name, body = {}, None, []
@@ -61,7 +62,7 @@ for fam, fname in FAMILIES.items():
         dn, mangled, lines, cnt = rows[0]
         w.write(f"\n## excerpt: {dn}\n")
         shown = set()
-        for mn in ("UTMALDG", "UBLKCP", "UTCHMMA", "UTCBAR", "LDTM", "UTMASTG"):
+        for mn in ("UTMALDG", "UBLKCP", "UTCHMMA", "UTCBAR", "LDTM", "UTMASTG", "LDGSTS", "LDSM", "HMMA"):
             for i, l in enumerate(lines):
                 if re.search(r"\b" + mn, l):
                     w.write(f"\n-- first {mn} (line {i}) --\n")
@@ -74,9 +75,9 @@ with open(os.path.join(OUT, "sass_summary.md"), "w") as w:
     w.write("UTCHMMA = tcgen05.mma (kind::f16), UTMALDG = cp.async.bulk.tensor (TMA), UBLKCP = cp.async.bulk, LDTM = tcgen05.ld, "
             "UTCBAR = tcgen05.commit, SYNCS = mbarrier.  Full excerpts: `sass_*.txt`.\n\n")
     for fam, rows in index:
-        w.write(f"## {fam} ({len(rows)} instantiations)\n\n| instantiation | " + " | ".join(MNEMONICS[:14]) + " |\n|---|" + "---|" * 14 + "\n")
+        w.write(f"## {fam} ({len(rows)} instantiations)\n\n| instantiation | " + " | ".join(MNEMONICS[:15]) + " |\n|---|" + "---|" * 15 + "\n")
         for dn, mangled, lines, cnt in rows[:40]:
             short = re.sub(r"^void ia::", "", dn).split("(")[0]
-            w.write(f"| `{short}` | " + " | ".join(str(cnt.get(m, 0)) for m in MNEMONICS[:14]) + " |\n")
+            w.write(f"| `{short}` | " + " | ".join(str(cnt.get(m, 0)) for m in MNEMONICS[:15]) + " |\n")
         w.write("\n")
 print("wrote", OUT)

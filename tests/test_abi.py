@@ -109,6 +109,14 @@ def _gloo_worker(rank, world, port, out_dir):
     s, i = formula.unpack_keys(merged)
     rs, ri = formula.topk_stable(qs @ cat.T, k)
     ok = np.array_equal(i, ri) and np.array_equal(s, rs.astype(np.float32))
+    # slice-wise merge: all-to-all hands every rank the lists of its slice of the (padded) queries
+    from item_alignment_b200 import all_to_all_keys
+    per = -(-q // world)
+    padded = np.zeros((per * world, k), dtype=np.uint64)
+    padded[:q] = local
+    mine = all_to_all_keys(torch.from_numpy(padded.view(np.int64))).numpy().view(np.uint64)      # [world, per, k]
+    merged_slice = formula.merge_topk_keys(mine, k)
+    ok = ok and np.array_equal(merged_slice[: max(0, min(per, q - rank * per))], merged[rank * per:(rank + 1) * per])
     open(os.path.join(out_dir, f"ok{rank}"), "w").write(str(bool(ok)))
     dist.destroy_process_group()
 

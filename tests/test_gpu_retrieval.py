@@ -196,10 +196,21 @@ def _nccl_worker(rank, world, port, out_dir):
     lo, hi = ia.shard_bounds(c_n, world, rank)
     dev = torch.device("cuda", rank)
     sharded = ia.ShardedCatalogIndex(cat[lo:hi].to(dev), c_n)
-    keys = sharded.topk_keys(q.to(dev), k, "cosine")
+    keys = sharded.topk_keys(q.to(dev), k, "cosine")                      # 200 queries: slice-wise merge (all-to-all + all-gather)
+    keys_odd = sharded.topk_keys(q[:131].to(dev), k, "cosine")             # odd count: padded slices
+    sharded.slice_merge = False
+    keys_ag = sharded.topk_keys(q.to(dev), k, "cosine")                   # one all-gather, every rank merges everything
+    # two query halves with the first half's exchange overlapped with the second half's scan (q >= 2048)
+    sharded.slice_merge = True
+    big_q = cat[torch.randint(0, c_n, (2300,), generator=gen)].to(dev)
+    keys_big = sharded.topk_keys(big_q, k, "cosine")
+    sharded.overlap = False
+    keys_big_serial = sharded.topk_keys(big_q, k, "cosine")
     with ia.CatalogIndex(cat.to(dev)) as whole:
         ref = whole.topk_keys(q.to(dev), k, "cosine")
-    ok = torch.equal(keys, ref)
+        ref_big = whole.topk_keys(big_q, k, "cosine")
+    ok = (torch.equal(keys, ref) and torch.equal(keys_ag, ref) and torch.equal(keys_odd, ref[:131]) and torch.equal(keys_big, ref_big)
+          and torch.equal(keys_big_serial, ref_big))
     sharded.close()
     open(os.path.join(out_dir, f"ok{rank}"), "w").write(str(bool(ok)))
     dist.destroy_process_group()
