@@ -13,11 +13,12 @@
 //     operand is the warp's slice of W held in registers, the two class rows split into three 16-bit terms (hi + lo + lo2 =
 //     the fp32 weight to 2^-24) in 6 of the 8 MMA columns.  The four partial logit tiles meet in shared memory (fixed order);
 //     warp 0 evaluates softmax / CE / delta for the 16 pairs (one pair per lane), writes logits / probs and publishes
-//     (p - label) and delta for the stage on an mbarrier; warps 1-3 meanwhile refill the stage the backward warps released.
+//     (p - label) and delta for the stage on an mbarrier.
 //   * BACKWARD warps 4-11 (each owns h/4 columns): ldmatrix.x4.trans + ONE mma per tile for dW (A = the tile transposed,
 //     B = (p - label) of the 16 pairs split three ways like W; fp32 accumulators for the warp's columns stay in registers
 //     for the whole kernel), and dx = delta * (W1 - W0) for its columns: 8 FMUL + 4 pack + one 16-byte store per lane and
-//     row -- the same fp32 product, rounded once, as the CUDA-core kernel.  Then they release the stage.
+//     row -- the same fp32 product, rounded once, as the CUDA-core kernel.  They release the stage right after the MMAs and
+//     refill it themselves (four rows per warp) before the stores.
 // Forward of group k+1 overlaps backward of group k: neither role's dependent chain (MMA -> exchange -> exp / log ->
 // stores) is on the other's critical path.  (A first, homogeneous version -- every warp doing every phase in lock-step with a
 // block barrier per group -- measured 130 us at h = 1024: 8 warps cannot hide a 9 000-cycle dependent chain per group.)
@@ -38,7 +39,7 @@ constexpr int FW = 4;            // forward warps
 constexpr int BW = 8;            // backward warps
 constexpr int RB = 16;           // pairs per stage (the M / K extent of one MMA)
 constexpr int THREADS = (FW + BW) * 32;
-constexpr int LOADERS = (FW - 1) * 32;   // threads that issue the cp.async of a stage (forward warps 1-3)
+constexpr int LOADERS = BW * 32;         // threads that issue the cp.async of a stage (the backward warps: they have the slack)
 }  // namespace hmma
 
 template <typename T> struct Mma16;
@@ -134,6 +135,36 @@ __global__ void __launch_bounds__(hmma::THREADS, 1) softmax_head_mma_kernel(cons
   const int lm = lane >> 3, lr = lane & 7;
   float loss_acc = 0.f, db_acc = 0.f;   // forward warp 0, lanes 0-15
 
+  // Stage fill by the BACKWARD warps (they wait for deltas a fifth of the time; the forward warps are the kernel's critical
+  // resource: with the fill on forward warps 1-3 they were busy 3 500 cycles per stage): loader warp lw copies rows lw, lw+8, lw+16,
+  // lw+24 of the 32-row stage (x rows 0-15, y rows 16-31), a warp instruction moves 512 contiguous bytes; loader 0 also brings
+  // the 16 labels.  Every thread's arrival on the stage's mbarrier fires when its own copies have landed.  Rows past the end are
+  // clamped to the last row: loaded, delta = 0, never stored.
+  auto issue = [&](int lw, int stage, int64_t grp) {
+    const uint32_t base = smem_base + (uint32_t)stage * STAGE_BYTES;
+#pragma unroll
+    for (int rr = 0; rr < 2 * RB / BW; ++rr) {
+      const int r = lw + rr * BW;
+      int64_t row = grp * RB + (r & 15);
+      if (row > p.n - 1) row = p.n - 1;
+      const uint4* src = reinterpret_cast<const uint4*>(r < 16 ? static_cast<const T*>(p.x) + row * p.ldx
+                                                                : static_cast<const T*>(p.y) + row * p.ldy);
+      const uint32_t dst = base + (uint32_t)r * PITCH + (uint32_t)lane * 16u;
+#pragma unroll
+      for (int v = 0; v < VPR / 32; ++v)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)v * 512u), "l"(src + lane + 32 * v) : "memory");
+    }
+    if (lw == 0 && lane < RB / 2) {
+      // the group's 16 labels ride along (two per lane; bytes past the end of the array are zero-filled, never read)
+      const int64_t l0 = grp * RB + 2 * lane;
+      const int64_t have = p.n - l0;
+      const uint32_t bytes = have >= 2 ? 16u : (have == 1 ? 8u : 0u);
+      const int64_t* src = p.labels + (bytes ? l0 : 0);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(base + LABEL_OFF + (uint32_t)lane * 16u), "l"(src), "r"(bytes) : "memory");
+    }
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[stage])) : "memory");
+  };
+
   if (w < FW) {
     // =========================================================================================== forward warps
     const int side = w >> 1;                          // 0: this warp's columns belong to x, 1: to y
@@ -156,38 +187,8 @@ __global__ void __launch_bounds__(hmma::THREADS, 1) softmax_head_mma_kernel(cons
     const float bias0 = __ldg(p.b), bias1 = __ldg(p.b + 1);
     const uint32_t off_n = (uint32_t)((lr + (lm & 1) * 8) * (int)PITCH + (lm >> 1) * 16);
     const uint32_t tile_base = (uint32_t)side * RB * PITCH + (uint32_t)col_base * 2u;
-    // stage fill by warps 1-3: warp w copies rows (w-1), (w-1)+3, ... of the 32-row stage (x rows 0-15, y rows 16-31); a warp
-    // instruction moves 512 contiguous bytes.  Rows past the end are clamped to the last row: loaded, delta = 0, never stored.
-    auto issue = [&](int stage, int64_t grp) {
-      const uint32_t base = smem_base + (uint32_t)stage * STAGE_BYTES;
-      for (int r = w - 1; r < 2 * RB; r += FW - 1) {
-        int64_t row = grp * RB + (r & 15);
-        if (row > p.n - 1) row = p.n - 1;
-        const uint4* src = reinterpret_cast<const uint4*>(r < 16 ? static_cast<const T*>(p.x) + row * p.ldx
-                                                                  : static_cast<const T*>(p.y) + row * p.ldy);
-        const uint32_t dst = base + (uint32_t)r * PITCH + (uint32_t)lane * 16u;
-#pragma unroll
-        for (int v = 0; v < VPR / 32; ++v)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)v * 512u), "l"(src + lane + 32 * v) : "memory");
-      }
-      if (w == 1 && lane < RB / 2) {
-        // the group's 16 labels ride along (two per lane; bytes past the end of the array are zero-filled, never read)
-        const int64_t l0 = grp * RB + 2 * lane;
-        const int64_t have = p.n - l0;
-        const uint32_t bytes = have >= 2 ? 16u : (have == 1 ? 8u : 0u);
-        const int64_t* src = p.labels + (bytes ? l0 : 0);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(base + LABEL_OFF + (uint32_t)lane * 16u), "l"(src), "r"(bytes) : "memory");
-      }
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[stage])) : "memory");
-    };
-    if (w >= 1) {
-      for (int s = 0; s < STAGES; ++s) {
-        const int64_t grp = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
-        if (grp < n_groups) issue(s, grp);
-      }
-    }
     int it = 0;
-    long long c_full = 0, c_bar = 0, c_empty = 0, c_soft = 0;
+    long long c_full = 0, c_bar = 0, c_soft = 0;
     const long long c_begin = clock64();
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++it) {
       const int stage = it % STAGES;
@@ -270,21 +271,11 @@ __global__ void __launch_bounds__(hmma::THREADS, 1) softmax_head_mma_kernel(cons
         __syncwarp();
         if (lane == 0) mbar_arrive(&dready[stage]);     // release: the deltas (and, transitively, the rows) are visible
         c_soft += clock64() - c0;
-      } else if (it >= 1) {
-        // ---- refill the stage of the previous group once the backward warps have released it
-        const int64_t gn = grp + (int64_t)(STAGES - 1) * gridDim.x;
-        if (gn < n_groups) {
-          const int sp = (it - 1) % STAGES;
-          mbar_wait(&empty[sp], (uint32_t)((it - 1) / STAGES) & 1u);
-          c_empty += clock64() - c0;
-          issue(sp, gn);
-        }
       }
     }
     if ((p.load_mode & 16) && lane == 0) {
       atomicAdd(&g_head_stats[0], (unsigned long long)c_full);
       atomicAdd(&g_head_stats[1], (unsigned long long)c_bar);
-      atomicAdd(&g_head_stats[2], (unsigned long long)c_empty);
       atomicAdd(&g_head_stats[3], (unsigned long long)(clock64() - c_begin));
       atomicAdd(&g_head_stats[6], (unsigned long long)c_soft);
     }
@@ -310,6 +301,11 @@ __global__ void __launch_bounds__(hmma::THREADS, 1) softmax_head_mma_kernel(cons
         const float4 a = __ldg(reinterpret_cast<const float4*>(w0 + e)), c = __ldg(reinterpret_cast<const float4*>(w0 + H2 + e));
         wd[e] = c.x - a.x; wd[e + 1] = c.y - a.y; wd[e + 2] = c.z - a.z; wd[e + 3] = c.w - a.w;
       }
+      // pin the eight differences in registers: left alone, the compiler re-materialises them inside the store loop (read-only
+      // loads may legally be repeated) and the backward warps then stall on L2 loads in their hot loop (23 % of the kernel's
+      // stall samples sat on the multiply below)
+#pragma unroll
+      for (int e = 0; e < E; ++e) asm volatile("" : "+f"(wd[e]));
     }
     const uint32_t m0 = g == 0 ? 0xffffffffu : 0u, m1 = g == 1 ? 0xffffffffu : 0u, m2 = g == 2 ? 0xffffffffu : 0u;
     float acc[TPW][4];
@@ -319,8 +315,12 @@ __global__ void __launch_bounds__(hmma::THREADS, 1) softmax_head_mma_kernel(cons
     const uint32_t tile_base = (uint32_t)side * RB * PITCH + (uint32_t)col_base * 2u;
     G* const gout = static_cast<G*>(side ? p.dy : p.dx);
     const int64_t ldg_out = side ? p.lddy : p.lddx;
+    for (int s = 0; s < STAGES; ++s) {
+      const int64_t grp = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+      if (grp < n_groups) issue(bw, s, grp);
+    }
     int it = 0;
-    long long c_wait = 0;
+    long long c_wait = 0, c_empty = 0;
     const long long c_begin = clock64();
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++it) {
       const int stage = it % STAGES;
@@ -364,6 +364,17 @@ __global__ void __launch_bounds__(hmma::THREADS, 1) softmax_head_mma_kernel(cons
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);        // this warp is done with the stage's rows and deltas
+      {
+        // refill: once ALL backward warps have released the stage (the forward warps finished with it before they published the
+        // deltas), this warp brings its four rows of group it + STAGES -- in flight during the stores below
+        const int64_t gn = grp + (int64_t)STAGES * gridDim.x;
+        if (gn < n_groups) {
+          const long long e0 = clock64();
+          mbar_wait(&empty[stage], par);
+          c_empty += clock64() - e0;
+          issue(bw, stage, gn);
+        }
+      }
       // ---- dx (or dy) of this warp's columns: one 16-byte (fp32 gradients: two) store per lane and row
       if (gout != nullptr && !(p.load_mode & 8)) {
         G* dst = gout + (grp * RB + row_par) * ldg_out + col_base + vec * E;
@@ -382,6 +393,7 @@ __global__ void __launch_bounds__(hmma::THREADS, 1) softmax_head_mma_kernel(cons
     }
     if ((p.load_mode & 16) && lane == 0) {
       atomicAdd(&g_head_stats[4], (unsigned long long)c_wait);
+      atomicAdd(&g_head_stats[2], (unsigned long long)c_empty);
       atomicAdd(&g_head_stats[5], (unsigned long long)(clock64() - c_begin));
     }
     // ---- dW partial of this CTA (columns of this warp) -> workspace

@@ -16,5 +16,5 @@ for dt, h in ((torch.bfloat16, 1024), (torch.bfloat16, 768), (torch.float16, 512
     fw, bw, ctas = 4, 8, 148
     tot_f, tot_b = out[3] / (fw * ctas), out[5] / (bw * ctas)
     print(f"h={h}: fwd warp {tot_f:9.0f} cyc: wait rows {out[0] / (fw * ctas) / tot_f * 100:5.1f} %  barrier {out[1] / (fw * ctas) / tot_f * 100:5.1f} %  "
-          f"loaders wait release {out[2] / (3 * ctas) / tot_f * 100:5.1f} %  warp0 softmax {out[6] / ctas / tot_f * 100:5.1f} %   |  "
+          f"bwd wait for release {out[2] / (bw * ctas) / tot_b * 100:5.1f} %  warp0 softmax {out[6] / ctas / tot_f * 100:5.1f} %   |  "
           f"bwd warp {tot_b:9.0f} cyc: wait deltas {out[4] / (bw * ctas) / tot_b * 100:5.1f} %")
