@@ -50,7 +50,7 @@ def timed_graph(fn, iters=30, warm=3):
     return e0.elapsed_time(e1) / iters * 1e3
 
 
-for dt, h in ((torch.bfloat16, 1024), (torch.bfloat16, 768), (torch.float32, 1024), (torch.float32, 768), (torch.float16, 512)):
+for dt, h in ((torch.bfloat16, 1024), (torch.bfloat16, 768), (torch.float32, 1024), (torch.float32, 768), (torch.float16, 512), (torch.bfloat16, 512)):
     x = torch.tanh(torch.randn(n, h, device=dev)).to(dt)
     y = torch.tanh(torch.randn(n, h, device=dev)).to(dt)
     l = (torch.rand(n, device=dev) < 0.5).long()
