@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <mutex>
 #include <new>
+#include <type_traits>
 
 #include "retrieval.cuh"
 
@@ -101,23 +102,34 @@ __device__ __forceinline__ float prefilter_threshold(float thr, float qinv) {
 
 // =============================================================================== tensor-core kernel
 namespace tc {
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int A_BYTES = BM * BK * 2;
 constexpr int THREADS = 192;
 constexpr int BUF_BYTES = BM * kBufPitch * 8;
 constexpr int CINV_BYTES = 2 * BN * 4;
-constexpr int SCR_BYTES = 0;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BUF_BYTES + CINV_BYTES + SCR_BYTES + 256 + 1024;  // + barriers + align slack
-static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
+// CTAS = 1: one CTA stages the 128-query tile and the whole 256-row catalog tile per k-block (48 KB, ring of 4).
+// CTAS = 2: a CTA PAIR (cluster of two SMs of one TPC) runs ONE 256 x 256 MMA per k-step (cta_group::2): each CTA stages ITS
+// 128-query tile and HALF of the catalog tile (32 KB, ring of 6) and ends up with the 128 x 256 accumulator of its own queries
+// in its own tensor memory -- a third less shared-memory fill per FLOP, half the catalog re-stream from L2 per query tile.
+template <int CTAS> struct Cfg {
+  static constexpr int B_ROWS = BN / CTAS;                       // catalog rows this CTA stages per k-block
+  static constexpr int STAGE_BYTES = A_BYTES + B_ROWS * BK * 2;
+  static constexpr int STAGES = CTAS == 1 ? 4 : 6;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BUF_BYTES + CINV_BYTES + 256 + 1024;  // + barriers + align slack
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
+};
 }  // namespace tc
+constexpr bool kPairDefault = false;   // the pair form is selected by default where use_pair() says it pays
 
 // KREG > 0: "small k" mode (k <= KREG): every thread keeps its query's top-KREG keys sorted in REGISTERS -- no append
 // buffers, no warp merges, no lists in L2 until the item ends.  Used for k <= 16 (probe passes, top-10 workloads).
-template <bool COSINE, int AB_FORMAT, int KREG>
+template <bool COSINE, int AB_FORMAT, int KREG, int CTAS>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                    const RetrParams p) {
   using namespace tc;
+  constexpr int STAGES = Cfg<CTAS>::STAGES, STAGE_BYTES = Cfg<CTAS>::STAGE_BYTES, B_ROWS = Cfg<CTAS>::B_ROWS;
+  constexpr int SCR_BYTES = 0;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzled operand tiles, keeping the pointer's shared-memory provenance
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -127,7 +139,7 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint64_t* full_bar = bars;                // [STAGES] TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;      // [STAGES] MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * STAGES;  // [2] MMA -> epilogue
-  uint64_t* tempty_bar = tfull_bar + 2;     // [2] epilogue -> MMA
+  uint64_t* tempty_bar = tfull_bar + 2;     // [2] epilogue -> MMA (pair: the epilogue warps of BOTH CTAs -> the leader's MMA thread)
   uint64_t* cfull_bar = tempty_bar + 2;     // [2] 1/|c| tile landed (bulk copy issued by the MMA thread)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(cfull_bar + 2);
 
@@ -138,32 +150,46 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_c);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); mbar_init(&cfull_bar[a], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4 * CTAS); mbar_init(&cfull_bar[a], 1); }
     fence_mbar_init();
   }
-  if (warp == w_mma) tmem_alloc(tmem_ptr, 512);
+  if (warp == w_mma) { if (CTAS == 1) tmem_alloc(tmem_ptr, 512); else tmem_alloc_pair(tmem_ptr, 512); }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 1) __syncthreads(); else cluster_sync();     // pair: the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const int n_items = p.n_qt * p.n_splits;
+  // Work items: (query tile [pair], catalog split).  The CTAs of a pair walk the same items; CTA `rank` owns query tile
+  // CTAS * slot + rank (an odd tile count leaves the last pair's second CTA a PHANTOM tile: operands zero-filled by TMA, nothing
+  // read from or written to global memory).  Lists / flags are indexed by item = split * n_qt + qt as in the single-CTA form.
+  const int rank = CTAS == 1 ? 0 : (int)cluster_ctarank();
+  const int unit = blockIdx.x / CTAS, n_units = gridDim.x / CTAS;
+  const int n_slots = (p.n_qt + CTAS - 1) / CTAS;
+  const int n_work = n_slots * p.n_splits;
 
   if (warp == w_tma) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int qt = item % p.n_qt, split = item / p.n_qt;
+      for (int work = unit; work < n_work; work += n_units) {
+        const int qt = (work % n_slots) * CTAS + rank, split = work / n_slots;
         const int t0 = split * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
         for (int t = t0; t < t1; ++t) {
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
             uint8_t* a_s = smem + stage * STAGE_BYTES;
-            tma_load_2d(a_s, &tmap_q, &full_bar[stage], kb * BK, qt * BM);
-            tma_load_2d(a_s + A_BYTES, &tmap_c, &full_bar[stage], kb * BK, t * BN);
+            if (CTAS == 1) {
+              mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+              tma_load_2d(a_s, &tmap_q, &full_bar[stage], kb * BK, qt * BM);
+              tma_load_2d(a_s + A_BYTES, &tmap_c, &full_bar[stage], kb * BK, t * BN);
+            } else {
+              // both CTAs' bytes are counted on the LEADER's barrier (the one its MMA thread waits on); the leader arms it
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CTAS * STAGE_BYTES);
+              const uint32_t bar0 = mapa_u32(smem_u32(&full_bar[stage]), 0);
+              tma_load_2d_pair(a_s, &tmap_q, bar0, kb * BK, qt * BM);
+              tma_load_2d_pair(a_s + A_BYTES, &tmap_c, bar0, kb * BK, t * BN + rank * B_ROWS);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -171,37 +197,60 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     }
   } else if (warp == w_mma) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(BM, BN, AB_FORMAT);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc(BM * CTAS, BN, AB_FORMAT);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int split = item / p.n_qt;
+      long long c_tempty = 0, c_full = 0;
+      const long long c_begin = clock64();
+      for (int work = unit; work < n_work; work += n_units) {
+        const int split = work / n_slots;
         const int t0 = split * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
         for (int t = t0; t < t1; ++t) {
+          long long c0 = clock64();
           mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator (and its 1/|c| tile)
+          c_tempty += clock64() - c0;
           tc_fence_after();
           if (COSINE) {   // this tile's inverse catalog norms ride along: 1 KB bulk copy, lands long before the MMAs finish
-            mbar_arrive_expect_tx(&cfull_bar[acc], BN * 4);
-            bulk_load_1d(cinv_s + acc * BN, p.cinv + (size_t)t * BN, BN * 4, &cfull_bar[acc]);
+            if (CTAS == 1) {
+              mbar_arrive_expect_tx(&cfull_bar[acc], BN * 4);
+              bulk_load_1d(cinv_s + acc * BN, p.cinv + (size_t)t * BN, BN * 4, &cfull_bar[acc]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < CTAS; ++c) {   // one copy into each CTA of the pair, armed and counted on that CTA's barrier
+                const uint32_t bar_c = mapa_u32(smem_u32(&cfull_bar[acc]), c);
+                mbar_arrive_expect_tx_cluster(bar_c, BN * 4);
+                bulk_load_1d_cluster(mapa_u32(smem_u32(cinv_s + acc * BN), c), p.cinv + (size_t)t * BN, BN * 4, bar_c);
+              }
+            }
           }
           const uint32_t d_tmem = tmem_base + acc * BN;
           for (int kb = 0; kb < p.kblocks; ++kb) {
+            c0 = clock64();
             mbar_wait(&full_bar[stage], phase);
+            c_full += clock64() - c0;
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
             const uint64_t a_desc = umma_smem_desc_sw128(a_addr);
             const uint64_t b_desc = umma_smem_desc_sw128(a_addr + A_BYTES);
 #pragma unroll
-            for (int k4 = 0; k4 < BK / 16; ++k4)   // +32 B (>>4 = 2) per K=16 step inside the swizzle atom
-              umma_f16(d_tmem, a_desc + 2 * k4, b_desc + 2 * k4, idesc, (kb | k4) != 0);
-            umma_commit(&empty_bar[stage]);          // smem slot free once these MMAs retire
+            for (int k4 = 0; k4 < BK / 16; ++k4) {   // +32 B (>>4 = 2) per K=16 step inside the swizzle atom
+              if (CTAS == 1) umma_f16(d_tmem, a_desc + 2 * k4, b_desc + 2 * k4, idesc, (kb | k4) != 0);
+              else umma_f16_pair(d_tmem, a_desc + 2 * k4, b_desc + 2 * k4, idesc, (kb | k4) != 0);
+            }
+            // smem slot free once these MMAs retire (pair: in both CTAs -- each producer waits on its own barrier)
+            if (CTAS == 1) umma_commit(&empty_bar[stage]); else umma_commit_pair(&empty_bar[stage], 3);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tfull_bar[acc]);              // accumulator complete
+          if (CTAS == 1) umma_commit(&tfull_bar[acc]); else umma_commit_pair(&tfull_bar[acc], 3);   // accumulator complete
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+      }
+      if (p.stats != nullptr && (p.flags & 128)) {   // flags bit 7: the MMA thread's waits replace the rare-path counters
+        atomicAdd(p.stats + 2, (unsigned long long)c_tempty);
+        atomicAdd(p.stats + 3, (unsigned long long)c_full);
+        atomicAdd(p.stats + 7, (unsigned long long)(clock64() - c_begin));
       }
     }
   } else {
@@ -214,20 +263,24 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const long long cyc_begin = clock64();
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int qt = item % p.n_qt, split = item / p.n_qt;
+    const uint32_t tempty_leader = CTAS == 1 ? 0u : mapa_u32(smem_u32(tempty_bar), 0);
+    for (int work = unit; work < n_work; work += n_units) {
+      const int qt = (work % n_slots) * CTAS + rank, split = work / n_slots;
+      const bool qt_ok = CTAS == 1 || qt < p.n_qt;     // false: phantom tile of an odd tile count (warp-uniform)
+      const int item = split * p.n_qt + qt;
       const int t0 = split * p.tiles_per_split;
       const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
       const int q_row = qt * BM + row_local;
-      const bool q_ok = q_row < p.q_rows;
+      const bool q_ok = q_row < p.q_rows;              // never true in a phantom tile
       float qinv = 1.f;
       if (COSINE) qinv = q_ok ? __ldg(p.qinv + q_row) : 0.f;
       uint64_t* lists_warp = p.lists + ((size_t)item * BM + e * 32) * kListCap;
-      for (int i = lane; i < 32 * kListCap; i += 32) lists_warp[i] = 0ull;
+      if (qt_ok)
+        for (int i = lane; i < 32 * kListCap; i += 32) lists_warp[i] = 0ull;
       __syncwarp();
       uint32_t* tau_warp = p.tau_global + qt * BM + e * 32;
       TopKThread st{0ull, 0};
-      if ((p.flags & 36) == 4) st.thr_key = finished_splits_bound(p, qt, split, e, row_local, BM);
+      if ((p.flags & 36) == 4 && qt_ok) st.thr_key = finished_splits_bound(p, qt, split, e, row_local, BM);
       uint64_t top[KREG > 0 ? KREG : 1];
 #pragma unroll
       for (int i = 0; i < (KREG > 0 ? KREG : 1); ++i) top[i] = 0ull;
@@ -238,13 +291,13 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const float* cs = cinv_s + acc * BN;
         // what other CTAs have published for this query: issue the (L2-latency) load now, consume it after the waits
         uint32_t tau_seen = 0;
-        if ((p.flags & 34) == 2) tau_seen = *reinterpret_cast<volatile uint32_t*>(tau_warp + lane);
+        if ((p.flags & 34) == 2 && qt_ok) tau_seen = *reinterpret_cast<volatile uint32_t*>(tau_warp + lane);
         const long long w0 = clock64();
         if (COSINE) mbar_wait(&cfull_bar[acc], acc_phase);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         cyc_wait += clock64() - w0;
-        if (!(p.flags & 34)) tau_seen = *reinterpret_cast<volatile uint32_t*>(tau_warp + lane);
+        if (!(p.flags & 34) && qt_ok) tau_seen = *reinterpret_cast<volatile uint32_t*>(tau_warp + lane);
         {
           const uint64_t gk = (uint64_t)tau_seen << 32;
           if (gk > st.thr_key) st.thr_key = gk;
@@ -256,7 +309,7 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         float thr_pre = thr_f;
         if (COSINE) thr_pre = prefilter_threshold(thr_f, qinv);
 #pragma unroll 1
-        for (int g = 0; g < BN / 32; ++g) {
+        for (int g = 0; g < ((p.flags & 64) ? 0 : BN / 32); ++g) {   // flags bit 6: skip the scan (mainloop ceiling; wrong results)
           uint32_t r[32];
           tmem_ld_32x32(taddr + g * 32, r);
           tmem_ld_wait();
@@ -339,7 +392,9 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // accumulator released: the MMA warp may overwrite it
+        if (lane == 0) {                                // accumulator released: the MMA warp may overwrite it
+          if (CTAS == 1) mbar_arrive(&tempty_bar[acc]); else mbar_arrive_cluster(tempty_leader + (uint32_t)acc * 8u);
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         // list maintenance OUTSIDE the accumulator's critical section: half-full buffers are merged now, while the
         // tensor core works on the next tiles, so that buffers rarely fill up (and force a merge) mid-tile
@@ -355,6 +410,7 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
       }
       __syncwarp();
+      if (!qt_ok) continue;     // phantom tile: nothing to publish
       if (KREG > 0) {
         // the register list becomes the item's list (positions >= KREG stay zero from the initialisation above)
         uint64_t* mine = lists_warp + (size_t)lane * kListCap;
@@ -379,22 +435,24 @@ retrieve_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       if (lane == 0) {
         atomicAdd(p.stats + 0, (unsigned long long)a);
         atomicAdd(p.stats + 1, (unsigned long long)stats.compactions);
-        atomicAdd(p.stats + 2, (unsigned long long)stats.rare_groups);
-        atomicAdd(p.stats + 3, (unsigned long long)stats.rare_blocks);
+        if (!(p.flags & 128)) {
+          atomicAdd(p.stats + 2, (unsigned long long)stats.rare_groups);
+          atomicAdd(p.stats + 3, (unsigned long long)stats.rare_blocks);
+        }
         atomicAdd(p.stats + 4, (unsigned long long)cyc_wait);
         atomicAdd(p.stats + 5, (unsigned long long)cyc_compact);
         atomicAdd(p.stats + 6, (unsigned long long)(clock64() - cyc_begin));
-        atomicAdd(p.stats + 7, (unsigned long long)cyc_rare);
+        if (!(p.flags & 128)) atomicAdd(p.stats + 7, (unsigned long long)cyc_rare);
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 1) __syncthreads(); else cluster_sync();   // pair: neither CTA leaves while the other may still touch its memory
   if (warp == w_mma) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (CTAS == 1) tmem_dealloc(tmem_base, 512); else tmem_dealloc_pair(tmem_base, 512);
   }
 }
 
@@ -712,7 +770,9 @@ struct ia_catalog {
   int device;
   float* cinv;          // [c]
   bool tc_ok;           // tensor-core path usable (16-bit dtype, TMA-compatible layout)
-  CUtensorMap tmap_c;
+  CUtensorMap tmap_c;        // box = 256 catalog rows x 64 columns
+  CUtensorMap tmap_c_half;   // box = 128 rows: what each CTA of a pair stages (cta_group::2 form of the kernel)
+  bool pair_ok;
   // lazily grown scratch
   uint64_t* lists; size_t lists_bytes;
   uint32_t* tau; size_t tau_bytes;      // [tau | done flags]
@@ -766,7 +826,7 @@ int ia_catalog_create(ia_catalog** out, int dtype, const void* catalog, int64_t 
   if (!cat) { set_error("out of host memory"); return IA_ERR_CUDA; }
   cat->dtype = dtype; cat->data = catalog; cat->c = c; cat->d = d; cat->ld = ld; cat->row_base = (uint32_t)row_base;
   cat->lists = nullptr; cat->lists_bytes = 0; cat->tau = nullptr; cat->tau_bytes = 0; cat->qinv = nullptr; cat->qinv_bytes = 0;
-  cat->cinv = nullptr; cat->tc_ok = false; cat->stats = nullptr; cat->bound = nullptr; cat->bound_bytes = 0;
+  cat->cinv = nullptr; cat->tc_ok = false; cat->pair_ok = false; cat->stats = nullptr; cat->bound = nullptr; cat->bound_bytes = 0;
   cudaGetDevice(&cat->device);
   cudaStream_t s = (cudaStream_t)stream;
   // inverse norms padded with zeros to whole 256-row tiles: the kernel bulk-copies one tile's worth at a time
@@ -785,6 +845,7 @@ int ia_catalog_create(ia_catalog** out, int dtype, const void* catalog, int64_t 
   if (e != cudaSuccess) { set_error("inverse-norm launch failed: %s", cudaGetErrorString(e)); cudaFree(cat->cinv); delete cat; return IA_ERR_CUDA; }
   if (dtype != IA_F32 && d % 8 == 0 && ld % 8 == 0 && reinterpret_cast<uintptr_t>(catalog) % 16 == 0) {
     if (make_tmap(&cat->tmap_c, dtype, catalog, c, d, ld, tc::BN) == IA_OK) cat->tc_ok = true;
+    cat->pair_ok = cat->tc_ok && make_tmap(&cat->tmap_c_half, dtype, catalog, c, d, ld, tc::BN / 2) == IA_OK;
   }
   *out = cat;
   return IA_OK;
@@ -806,21 +867,54 @@ int ia_catalog_topk(ia_catalog* cat, int measure, const void* queries, int64_t q
   return ia_catalog_topk_seeded(cat, measure, queries, q, ldq, k, nullptr, keys_out, stream);
 }
 
-// one launch of the tensor-core kernel for the decomposition in p
-static int launch_tc(ia_catalog* cat, int measure, bool kreg, const CUtensorMap& tmap_q, const RetrParams& p, int grid, cudaStream_t s) {
+// CTA-pair (cta_group::2) form of the tensor-core kernel: IA_RETR_PAIR=1 / 0 forces it on / off.  A pair shares every catalog
+// tile between two query tiles, so it needs at least two of them; an odd count wastes one tile of MMA work.
+static bool use_pair(const ia_catalog* cat, int n_qt) {
+  const char* e = getenv("IA_RETR_PAIR");     // read per call: tests and A/B runs switch it between calls
+  const int env = e ? atoi(e) : -1;
+  if (!cat->pair_ok || n_qt < 2 || (sm_count() & 1)) return false;
+  if (env >= 0) return env != 0;
+  return kPairDefault && (n_qt % 2 == 0 || n_qt >= 32);
+}
+
+// one launch of the tensor-core kernel for the decomposition in p; the grid is one CTA per SM or as many as there is work
+static int launch_tc(ia_catalog* cat, int measure, bool kreg, bool pair, const CUtensorMap& tmap_q, const RetrParams& p, cudaStream_t s) {
   const int fmt_bf16 = cat->dtype == IA_BF16;
-  auto launch = [&](auto kernel) -> int {
-    IA_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-    kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(tmap_q, cat->tmap_c, p);
+  const int sms = sm_count();
+  auto launch = [&](auto kernel, auto ctas_tag) -> int {
+    constexpr int CTAS = decltype(ctas_tag)::value;
+    constexpr int smem = tc::Cfg<CTAS>::SMEM_BYTES;
+    IA_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int64_t n_work = (int64_t)((p.n_qt + CTAS - 1) / CTAS) * p.n_splits;
+    const int units = (int)(n_work < sms / CTAS ? n_work : sms / CTAS);
+    if (CTAS == 1) {
+      kernel<<<units, tc::THREADS, smem, s>>>(tmap_q, cat->tmap_c, p);
+    } else {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(units * CTAS)); cfg.blockDim = dim3(tc::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      IA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmap_q, cat->tmap_c_half, p));
+    }
     IA_LAUNCH_CHECK();
     return IA_OK;
   };
+  using One = std::integral_constant<int, 1>;
+  using Two = std::integral_constant<int, 2>;
+#define IA_TC_DISPATCH(COS, KR)                                                                                               \
+  do {                                                                                                                        \
+    if (pair) return fmt_bf16 ? launch(retrieve_tc_kernel<COS, 1, KR, 2>, Two{}) : launch(retrieve_tc_kernel<COS, 0, KR, 2>, Two{}); \
+    return fmt_bf16 ? launch(retrieve_tc_kernel<COS, 1, KR, 1>, One{}) : launch(retrieve_tc_kernel<COS, 0, KR, 1>, One{});    \
+  } while (0)
   if (kreg) {
-    if (measure == IA_COSINE) return fmt_bf16 ? launch(retrieve_tc_kernel<true, 1, 16>) : launch(retrieve_tc_kernel<true, 0, 16>);
-    return fmt_bf16 ? launch(retrieve_tc_kernel<false, 1, 16>) : launch(retrieve_tc_kernel<false, 0, 16>);
+    if (measure == IA_COSINE) IA_TC_DISPATCH(true, 16);
+    IA_TC_DISPATCH(false, 16);
   }
-  if (measure == IA_COSINE) return fmt_bf16 ? launch(retrieve_tc_kernel<true, 1, 0>) : launch(retrieve_tc_kernel<true, 0, 0>);
-  return fmt_bf16 ? launch(retrieve_tc_kernel<false, 1, 0>) : launch(retrieve_tc_kernel<false, 0, 0>);
+  if (measure == IA_COSINE) IA_TC_DISPATCH(true, 0);
+  IA_TC_DISPATCH(false, 0);
+#undef IA_TC_DISPATCH
 }
 
 static int grow_scratch(ia_catalog* cat, int64_t n_items, int n_qt, int BM) {
@@ -847,7 +941,7 @@ static int probe_pass(ia_catalog* cat, int measure, const CUtensorMap& tmap_q, R
   IA_CUDA_CHECK(cudaMemsetAsync(cat->tau, 0, sizeof(uint32_t) * (tau_n + done_n), s));
   p.lists = cat->lists; p.overflow = nullptr; p.tau_global = cat->tau; p.done = cat->tau + tau_n; p.stats = nullptr;
   const int sms = sm_count();
-  if ((rc = launch_tc(cat, measure, true, tmap_q, p, (int)(n_items < sms ? n_items : sms), s)) != IA_OK) return rc;
+  if ((rc = launch_tc(cat, measure, true, use_pair(cat, p.n_qt), tmap_q, p, s)) != IA_OK) return rc;
   const int64_t want = (q + 255) / 256;
   probe_bound_kernel<<<(int)(want < 4 * sms ? want : 4 * sms), 256, 0, s>>>(cat->lists, groups, p.n_qt, tc::BM, kp, q, cat->bound, bound_i64);
   IA_LAUNCH_CHECK();
@@ -910,7 +1004,10 @@ static int catalog_topk_impl(ia_catalog* cat, int measure, float dist_eps, int d
   double penalty = (use_tc ? 0.3 : 0.15) * k;
   if (use_tc && (tau_init != nullptr || use_kreg || seeded_by_probe)) penalty = 2.0 + 0.03 * k;
   if (const char* f = getenv("IA_RETR_PENALTY")) penalty = atof(f) * k;
-  plan_splits(p.n_qt, p.n_tiles, ctas, use_tc ? 8 : 4, penalty, &p.n_splits, &p.tiles_per_split);
+  // a CTA pair is one scheduling unit that takes two query tiles through a split
+  const bool pair = use_tc && use_pair(cat, p.n_qt);
+  if (pair) plan_splits((p.n_qt + 1) / 2, p.n_tiles, ctas / 2, 8, penalty, &p.n_splits, &p.tiles_per_split);
+  else plan_splits(p.n_qt, p.n_tiles, ctas, use_tc ? 8 : 4, penalty, &p.n_splits, &p.tiles_per_split);
   const int64_t n_items = (int64_t)p.n_qt * p.n_splits;
 
   if ((rc = grow_scratch(cat, n_items, p.n_qt, BM)) != IA_OK) return rc;
@@ -930,7 +1027,7 @@ static int catalog_topk_impl(ia_catalog* cat, int measure, float dist_eps, int d
   const int grid = (int)(n_items < ctas ? n_items : ctas);
 
   if (use_tc) {
-    if ((rc = launch_tc(cat, measure, use_kreg, tmap_q, p, grid, s)) != IA_OK) return rc;
+    if ((rc = launch_tc(cat, measure, use_kreg, pair, tmap_q, p, s)) != IA_OK) return rc;
   } else {
     auto launch = [&](auto kernel, auto* tq) -> int {
       using TP = decltype(tq);

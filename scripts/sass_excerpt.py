@@ -18,7 +18,7 @@ OUT = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles", "r02"
 FAMILIES = {"retrieve_tc_kernel": "sass_retrieve_tc_kernel.txt", "project_kernel": "sass_project_kernel.txt",
             "wgrad_kernel": "sass_wgrad_kernel.txt", "softmax_head_mma_kernel": "sass_softmax_head_mma_kernel.txt",
             "radix_scatter_kernel": None, "pair_kernel": None, "softmax_head_kernel": None}
-MNEMONICS = ("UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "STTM", "UTCBAR", "SYNCS", "UTCATOMSWS", "LDGSTS", "LDSM", "HMMA",
+MNEMONICS = ("UTCHMMA", "UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "UTCBAR.2CTA", "UTCQMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "STTM", "UTCBAR", "SYNCS", "UTCATOMSWS", "LDGSTS", "LDSM", "HMMA",
              "MATCH", "REDUX", "LDG.E.128", "STG.E.128", "LDS.128", "MUFU", "IMAD", "FFMA")
 
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout

@@ -256,3 +256,49 @@ def test_single_gpu_probed_topk_equals_plain_topk():
     with pytest.raises(ValueError):
         with ia.CatalogIndex(cat[:5000].to(DEV)) as small:
             small.probe_bound(qd, 13, 4, 2048, "cosine")            # 4 x 2048 rows do not fit into 5000
+
+
+@pytest.fixture
+def pair_env():
+    old = os.environ.get("IA_RETR_PAIR")
+    yield
+    if old is None:
+        os.environ.pop("IA_RETR_PAIR", None)
+    else:
+        os.environ["IA_RETR_PAIR"] = old
+
+
+@pytest.mark.parametrize("dt,q_n,c_n,d,k,measure", [
+    (torch.bfloat16, 256, 4096, 64, 10, "inner_product"),      # two query tiles: one pair, register top-k path
+    (torch.bfloat16, 300, 5000, 128, 10, "cosine"),            # three tiles: the second pair's peer CTA runs a phantom tile
+    (torch.float16, 1000, 70000, 256, 100, "cosine"),          # probe pass + append / merge path, ragged last catalog tile
+    (torch.bfloat16, 129, 100000, 512, 32, "inner_product"),   # a one-row second tile
+    (torch.bfloat16, 2100, 200000, 1024, 128, "cosine"),       # 17 tiles, k at the list capacity
+])
+def test_cta_pair_kernel_equals_single_cta_kernel(pair_env, dt, q_n, c_n, d, k, measure):
+    """The cta_group::2 form of the tensor-core kernel (IA_RETR_PAIR=1: a pair of CTAs runs one 256 x 256 MMA, each CTA keeps the
+    128 x 256 accumulator of its own query tile) must return the keys of the single-CTA form bit for bit -- also when seeded
+    -- and both must agree with the oracle."""
+    import item_alignment_b200 as ia
+    from oracle import torch_port
+    gen = torch.Generator().manual_seed(q_n + c_n + d + k)
+    cat = torch.tanh(torch.randn(c_n, d, generator=gen)).to(dt)
+    q = torch.tanh(cat[torch.randint(0, c_n, (q_n,), generator=gen)].float() + 0.1 * torch.randn(q_n, d, generator=gen)).to(dt)
+    cat[c_n // 2: c_n // 2 + 50] = cat[:50]
+    qd = q.to(DEV)
+    with ia.CatalogIndex(cat.to(DEV)) as index:
+        out = {}
+        for pair in ("0", "1"):
+            os.environ["IA_RETR_PAIR"] = pair
+            out[pair] = index.topk_keys(qd, k, measure)
+            out[pair + "plain"] = index.topk_keys_unprobed(qd, k, measure)
+            torch.cuda.synchronize()
+        assert torch.equal(out["0"], out["1"])
+        assert torch.equal(out["0plain"], out["1plain"])
+        assert torch.equal(out["0"], out["0plain"])
+        os.environ["IA_RETR_PAIR"] = "1"
+        scores, rows = index.topk(qd, k, measure)
+        if q_n * c_n <= 1000 * 70000:
+            ref = torch.cat([torch_port.all_pairs_scores(measure, q[i:i + 64], cat) for i in range(0, q_n, 64)]).numpy()
+            tol = 4e-6 * max(float(np.abs(ref).max()), 1.0)
+            parity.assert_topk_matches(scores, rows, ref, k, True, tol=tol)
