@@ -58,3 +58,24 @@ with ia.CatalogIndex(cat) as index:
                 print(f"k={k:3d} pair={pair} {ms:7.3f} ms  {2.0 * Q * C * D / ms / 1e9:7.0f} TFLOP/s  appends/query {st['appends'] / Q:6.0f}  merges/query {st['compactions'] / Q:5.1f}  "
                       f"splits {st['splits']}x{st['tiles_per_split']}", flush=True)
         print("   identical keys:", bool(torch.equal(res["0"], res["1"])))
+
+# a slice of BASELINE config 5 (100 000 queries x 512, top-10, inner product): 2 M of a shard's 12.5 M rows
+del cat, q
+C, Q, D = 2_000_000, 100_000, 512
+cat = torch.empty(C, D, dtype=torch.bfloat16, device=dev)
+for s in range(0, C, 131072):
+    cat[s:s + 131072] = torch.tanh(torch.randn(min(131072, C - s), D, device=dev, generator=gen)).to(torch.bfloat16)
+q = torch.tanh(torch.randn(Q, D, device=dev, generator=gen)).to(torch.bfloat16)
+with ia.CatalogIndex(cat) as index:
+    res = {}
+    for rep in range(2):
+        for pair in ("0", "1"):
+            os.environ["IA_RETR_PAIR"] = pair
+            ts = []
+            for it in range(4):
+                e0.record(); keys = index.topk_keys(q, 10, "inner_product"); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+            st = index.last_stats()
+            ms = statistics.median(ts[1:])
+            res[pair] = keys
+            print(f"C5 slice (2M x 512, 100k queries, k=10) pair={pair} {ms:8.3f} ms  {2.0 * Q * C * D / ms / 1e9:7.0f} TFLOP/s  splits {st['splits']}x{st['tiles_per_split']}", flush=True)
+    print("   identical keys:", bool(torch.equal(res["0"], res["1"])))
