@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/ia_b200.h"
 
@@ -35,6 +36,39 @@ int device_slot();  // index of the current device in [0, kMaxDevices): per-devi
     ia::g_launches.fetch_add(1);              \
     IA_CUDA_CHECK(cudaGetLastError());        \
   } while (0)
+
+// Programmatic dependent launch: the grid may be SCHEDULED while its predecessor in the stream is still draining (its CTAs take
+// the SM slots the predecessor's CTAs leave), and every kernel launched this way executes pdl_wait() before its first global
+// memory access -- that returns when the predecessor has completed and its writes are visible, so the stream's ordering is
+// unchanged; what overlaps is launch latency, CTA scheduling and the prologue.  pdl_trigger() at the top of a kernel lets ITS
+// successor do the same.  IA_PDL=0 launches the plain way (A/B runs).
+inline bool pdl_enabled() {
+  static const int on = [] { const char* e = getenv("IA_PDL"); return e ? atoi(e) : 1; }();
+  return on != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args... args) {
+  if (!pdl_enabled()) {
+    kernel<<<grid, block, smem, stream>>>(args...);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+#define IA_PDL_LAUNCH_CHECK(expr)             \
+  do {                                        \
+    ia::g_launches.fetch_add(1);              \
+    IA_CUDA_CHECK(expr);                      \
+  } while (0)
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 template <typename K>
 int blocks_per_sm(K kernel, int threads, size_t smem = 0) {

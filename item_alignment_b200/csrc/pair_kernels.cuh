@@ -124,6 +124,8 @@ constexpr int kBulkStages = 3;
 template <typename T, typename G, int MEASURE, int MODE, bool COSLOSS, int VPL, bool BULK, int ROWS, bool ACT = false>
 __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
   static_assert(!BULK || ROWS == 1, "the bulk ring feeds one row per iteration");
+  pdl_wait();       // launched with programmatic stream serialization (launch_pdl): nothing is read before the predecessor is done
+  pdl_trigger();
   constexpr int E = VecTraits<T>::kElems;
   constexpr bool kGradCosForm = COSLOSS || MEASURE == IA_INNER || MEASURE == IA_COSINE;
   const int lane = threadIdx.x & 31;
@@ -365,6 +367,8 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
 // Any D, any alignment: scalar loads, two sweeps over the row (the second one hits L1/L2).
 template <typename T, typename G, int MEASURE, int MODE, bool COSLOSS, bool ACT = false>
 __global__ void __launch_bounds__(256) pair_kernel_generic(const PairParams p) {
+  pdl_wait();
+  pdl_trigger();
   constexpr bool kGradCosForm = COSLOSS || MEASURE == IA_INNER || MEASURE == IA_COSINE;
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
@@ -481,8 +485,7 @@ int launch_rows(const PairParams& p, cudaStream_t stream) {
   if (cap > kMaxPartials) cap = kMaxPartials;
   int grid = (int)(want < cap ? want : cap);
   if (grid < 1) grid = 1;
-  kernel<<<grid, kThreads, 0, stream>>>(p);
-  IA_LAUNCH_CHECK();
+  IA_PDL_LAUNCH_CHECK(launch_pdl(kernel, grid, kThreads, 0, stream, p));
   return IA_OK;
 }
 
@@ -506,8 +509,7 @@ int launch_rows_bulk(const PairParams& p, size_t elem_size, cudaStream_t stream)
   if (cap > kMaxPartials) cap = kMaxPartials;
   int grid = (int)(want < cap ? want : cap);
   if (grid < 1) grid = 1;
-  kernel<<<grid, kThreads, smem, stream>>>(p);
-  IA_LAUNCH_CHECK();
+  IA_PDL_LAUNCH_CHECK(launch_pdl(kernel, grid, kThreads, smem, stream, p));
   return IA_OK;
 }
 

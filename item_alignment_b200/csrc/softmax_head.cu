@@ -43,6 +43,7 @@ constexpr int kHeadMaxStages = 4;   // rows in flight per warp in the bulk-copy 
 // kernel is bound by dependent-issue latency, not by bandwidth.
 template <typename T, typename G, bool TRAIN, int VPL, int RR, bool FULL, int NW, bool REREAD>
 __global__ void __launch_bounds__(NW * 32, TRAIN ? 1 : 2) softmax_head_kernel(const HeadParams p) {
+  pdl_wait();       // launched with programmatic stream serialization (launch_pdl)
   constexpr int E = VecTraits<T>::kElems;
   constexpr int C = E / 4;            // float4 chunks per 128-bit input vector
   constexpr int P4 = VPL * 32 * C;    // float4 per (padded) weight-row half
@@ -336,6 +337,9 @@ __global__ void __launch_bounds__(NW * 32, TRAIN ? 1 : 2) softmax_head_kernel(co
       for (int w = 0; w < NW; ++w) { blk += (double)wl[w]; dbs += wdb[w]; }
       part[h2] = dbs;
     }
+    // the dW finalize launch may be scheduled from here on (it waits for this grid to complete before it reads the partials).
+    // Not earlier: its CTAs would sit next to this kernel's for the whole run (measured: 72 -> 75 us at h = 768).
+    pdl_trigger();
     grid_sum_finish(blk, p.workspace, p.loss_out, p.loss_scale);
   }
 }
@@ -344,6 +348,8 @@ __global__ void __launch_bounds__(NW * 32, TRAIN ? 1 : 2) softmax_head_kernel(co
 // dW[0] = -dW[1]; same for db.  One warp per column.
 __global__ void __launch_bounds__(256) softmax_head_finalize(const float* partials, int nblocks, int h2, float* dw,
                                                              float* db, const float* upstream, int skip_one) {
+  pdl_wait();       // scheduled while the main kernel drains; the partials are read only once it has completed
+  pdl_trigger();
   if (upstream != nullptr && skip_one && __ldg(upstream) == 1.0f) return;   // the main kernel left at once: no new partials
   const int lane = threadIdx.x & 31;
   const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -379,13 +385,11 @@ static int launch_head_rr(const HeadParams& p_in, int stages, size_t smem, cudaS
   int64_t cap = (int64_t)sm_count() * (TRAIN ? 1 : blocks_per_sm(kernel, NW * 32, smem));
   if (cap > kHeadMaxGrid) cap = kHeadMaxGrid;
   const int grid = (int)(want < cap ? want : cap);
-  kernel<<<grid, NW * 32, smem, stream>>>(p);
-  IA_LAUNCH_CHECK();
+  IA_PDL_LAUNCH_CHECK(launch_pdl(kernel, grid, NW * 32, smem, stream, p));
   if (TRAIN && (dw || db)) {
     const float* partials = reinterpret_cast<const float*>(static_cast<const char*>(p.workspace) + kWorkspaceBytes);
     const int h2 = 2 * p.h;
-    softmax_head_finalize<<<(h2 + 1 + 7) / 8, 256, 0, stream>>>(partials, grid, h2, dw, db, p.upstream, p.upstream_skip_one);
-    IA_LAUNCH_CHECK();
+    IA_PDL_LAUNCH_CHECK(launch_pdl(softmax_head_finalize, (h2 + 1 + 7) / 8, 256, 0, stream, partials, grid, h2, dw, db, p.upstream, p.upstream_skip_one));
   }
   return IA_OK;
 }

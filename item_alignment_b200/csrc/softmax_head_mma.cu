@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(hmma::THREADS, 1) softmax_head_mma_kernel(cons
   constexpr uint32_t LABEL_OFF = 2u * RB * PITCH, STAGE_BYTES = LABEL_OFF + RB * 8u;   // [x rows | y rows | 16 int64 labels]
   constexpr int VPR = H / 8;           // 16-byte vectors per row
   constexpr int STAGES = stages_for(TPW);
+  pdl_wait();       // launched with programmatic stream serialization (launch_pdl)
   float gscale = p.grad_scale;
   if (p.upstream != nullptr) {   // gradient recomputation with the upstream scalar folded in before the one rounding
     const float u = __ldg(p.upstream);
@@ -425,6 +426,7 @@ __global__ void __launch_bounds__(hmma::THREADS, 1) softmax_head_mma_kernel(cons
     }
   }
   __syncthreads();
+  pdl_trigger();    // the dW finalize launch may be scheduled now (not earlier: its waiting CTAs would share the SMs with this kernel)
   grid_sum_finish((double)s_loss, p.workspace, p.loss_out, p.loss_scale);
 }
 
@@ -456,13 +458,11 @@ static int launch_mma(const HeadParams& p, cudaStream_t stream, float* dw, float
     IA_CUDA_CHECK(cudaGetSymbolAddress(&sp, g_head_stats));
     IA_CUDA_CHECK(cudaMemsetAsync(sp, 0, sizeof(unsigned long long) * 8, stream));
   }
-  kernel<<<grid, THREADS, smem, stream>>>(pd);
-  IA_LAUNCH_CHECK();
+  IA_PDL_LAUNCH_CHECK(launch_pdl(kernel, grid, (int)THREADS, smem, stream, pd));
   if (dw || db) {
     const float* partials = reinterpret_cast<const float*>(static_cast<const char*>(p.workspace) + kWorkspaceBytes);
     const int h2 = 2 * p.h;
-    softmax_head_finalize<<<(h2 + 1 + 7) / 8, 256, 0, stream>>>(partials, grid, h2, dw, db, p.upstream, p.upstream_skip_one);
-    IA_LAUNCH_CHECK();
+    IA_PDL_LAUNCH_CHECK(launch_pdl(softmax_head_finalize, (h2 + 1 + 7) / 8, 256, 0, stream, partials, grid, h2, dw, db, p.upstream, p.upstream_skip_one));
   }
   return IA_OK;
 }
